@@ -1,0 +1,344 @@
+// Scalar muon DCS arithmetic shared by every kernel in dcs_kernels.cu.
+//
+// Each function evaluates the same sequence of IEEE-754 double operations as the reference's CPU
+// code (cited per function, paths relative to the reference tree), with two changes that do not
+// alter a single bit of the result:
+//   * sub-expressions that depend only on (element, projectile mass) are evaluated once on the
+//     host (dcs_params.hh) with the same operand order and handed over in `Params`;
+//   * exp/log/log10 are glibm:: (glibm.cuh), the table-driven routines glibc itself runs.
+// Division and sqrt are CUDA's IEEE-correct ones.  The translation unit is compiled with
+// -fmad=false so that no multiply-add is contracted; the reference's benchmark/test builds
+// (-O3, x86-64 baseline) contain no FMA either.
+//
+// The header also compiles for the host (g++ -ffp-contract=off -mfma) so oracle/hostcheck.cc can
+// compare it with the oracle without a GPU.  That host build is a test fixture only; the product
+// has no CPU path.
+#pragma once
+
+#include "glibm.cuh"
+
+namespace noa_b200 {
+
+constexpr double kElectronMass = 0.510998910E-03;   // src/noa/pms/physics.hh:57
+constexpr double kAvogadro = 6.02214076E+23;        // src/noa/pms/physics.hh:54
+constexpr double kXFraction = 5E-02;                // src/noa/pms/physics.hh:76
+
+// Everything that depends only on the atomic element and the projectile mass.
+// Filled by make_params() in dcs_params.hh (host, same libm as the reference's CPU path).
+struct Params {
+    double A, I, mass, Zd;
+    int32_t Z;
+    int32_t z_is_one;
+    // bremsstrahlung (src/noa/pms/physics.hh:119-133)
+    double b_bzn, b_bze, b_dn, b_phie, b_pref, b_hm2, b_c1, b_bzem;
+    // pair production (src/noa/pms/dcs.hh:153-166, 235-241, 255)
+    double p_z13, p_thr, p_r, p_r2, p_hr2, p_az13, p_cl, p_cle, p_raz13, p_z15, p_g1, p_g2, p_cz;
+    // photonuclear (src/noa/pms/dcs.hh:290, 313-315, 349, 374)
+    double n_logA, n_logq0l, n_alow, n_halfA, n_2m2, n_m2, n_qpi;
+    // ionisation (src/noa/pms/dcs.hh:422, 431, 435-436)
+    double i_wmin, i_kthr, i_m2;
+};
+
+// ---- quadrature rules (src/noa/utils/numerics.hh:97-100, 116-121, 137-144) -------------------
+#define NOA_GL6_X {0.03376524, 0.16939531, 0.38069041, 0.61930959, 0.83060469, 0.96623476}
+#define NOA_GL6_W {0.08566225, 0.18038079, 0.23395697, 0.23395697, 0.18038079, 0.08566225}
+#define NOA_GL8_X {0.01985507, 0.10166676, 0.2372338, 0.40828268, 0.59171732, 0.7627662, \
+                   0.89833324, 0.98014493}
+#define NOA_GL8_W {0.05061427, 0.11119052, 0.15685332, 0.18134189, 0.18134189, 0.15685332, \
+                   0.11119052, 0.05061427}
+#define NOA_GL9_X {0.0000000000000000, -0.8360311073266358, 0.8360311073266358,               \
+                   -0.9681602395076261, 0.9681602395076261, -0.3242534234038089,              \
+                   0.3242534234038089, -0.6133714327005904, 0.6133714327005904}
+#define NOA_GL9_W {0.3302393550012598, 0.1806481606948574, 0.1806481606948574,                \
+                   0.0812743883615744, 0.0812743883615744, 0.3123470770400029,                \
+                   0.3123470770400029, 0.2606106964029354, 0.2606106964029354}
+
+// ------------------------------------------------------------------------------------------
+// Bremsstrahlung -- src/noa/pms/physics.hh:114-153
+// ------------------------------------------------------------------------------------------
+NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tables &T) {
+    const double me = kElectronMass;
+    const double sqrte = 1.648721271;
+    const double E = K + p.mass;
+    const double delta_factor = p.b_hm2 / E;
+    const double qe_max = E / (1. + p.b_hm2 / (me * E));
+    const double nu = q / E;
+    const double delta = delta_factor * nu / (1. - nu);
+    double phi_n = glibm::log(p.b_bzn * (p.mass + delta * p.b_c1) /
+                                  (p.b_dn * (me + delta * sqrte * p.b_bzn)),
+                              T.log_tab);
+    if (phi_n < 0.) phi_n = 0.;
+    double phi_e = 0.;
+    if (q < qe_max) {
+        phi_e = glibm::log(p.b_bzem / ((1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)),
+                           T.log_tab);
+        if (phi_e < 0.) phi_e = 0.;
+    }
+    const double s = p.b_pref * (p.Zd * phi_n + phi_e) * (4. / 3. * (1. / nu - 1.) + nu);
+    return (s < 0.) ? 0. : s * 1E+03 * kAvogadro / p.A;
+}
+
+// ------------------------------------------------------------------------------------------
+// e+e- pair production -- src/noa/pms/dcs.hh:144-258
+// ------------------------------------------------------------------------------------------
+struct PairKinematics {   // per-(K,q) quantities of src/noa/pms/dcs.hh:159-176
+    double tmin, beta, xi_factor, gamma;
+};
+
+// Kinematic window and integration bound; false = the DCS is exactly 0 (dcs.hh:151-156,174-175)
+NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tables &T,
+                       PairKinematics &k) {
+    if (q <= 4. * kElectronMass) return false;
+    if (q >= K + p.p_thr) return false;
+    const double nu = q / (K + p.mass);
+    k.beta = 0.5 * nu * nu / (1. - nu);
+    k.xi_factor = p.p_hr2 * k.beta;
+    k.gamma = 1. + K / p.mass;
+    const double x0 = 4. * kElectronMass / q;
+    const double x1 = 6. / (k.gamma * (k.gamma - q / p.mass));
+    const double argmin = (x0 + 2. * (1. - x0) * x1) / (1. + (1. - x1) * sqrt(1. - x0));
+    if ((argmin >= 1.) || (argmin <= 0.)) return false;
+    k.tmin = glibm::log(argmin, T.log_tab);
+    return true;
+}
+
+// Integrand of the t = ln(1-rho) integral at node t (dcs.hh:179-227)
+NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Params &p,
+                        const glibm::Tables &T) {
+    const double beta = k.beta;
+    const double eps = glibm::exp(t * k.tmin, T.exp_tab);
+    const double rho = 1. - eps;
+    const double rho2 = rho * rho;
+    const double rho21 = eps * (2. - eps);
+    const double xi = k.xi_factor * rho21;
+    const double xi_i = 1. / xi;
+
+    double Be;
+    if (xi >= 1E+03)
+        Be = 0.5 * xi_i * ((3 - rho2) + 2. * beta * (1. + rho2));
+    else
+        Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) * glibm::log(1. + xi_i, T.log_tab) +
+             (rho21 - beta) / (1. + xi) - 3. - rho2;
+    const double Ye = (5. - rho2 + 4. * beta * (1. + rho2)) /
+                      (2. * (1. + 3. * beta) * glibm::log(3. + xi_i, T.log_tab) - rho2 -
+                       2. * beta * (2. - rho2));
+    const double xe = (1. + xi) * (1. + Ye);
+    const double cLi = p.p_cl / rho21;
+    const double Le = glibm::log(p.p_az13 * sqrt(xe) * q / (q + cLi * xe), T.log_tab) -
+                      0.5 * glibm::log(1. + p.p_cle * xe, T.log_tab);
+    double phi_e = Be * Le;
+    if (phi_e < 0.) phi_e = 0.;
+
+    double Bmu;
+    if (xi <= 1E-03)
+        Bmu = 0.5 * xi * (5. - rho2 + beta * (3. + rho2));
+    else
+        Bmu = ((1. + rho2) * (1. + 1.5 * beta) - xi_i * (1. + 2. * beta) * rho21) *
+                  glibm::log(1. + xi, T.log_tab) +
+              xi * (rho21 - beta) / (1. + xi) + (1. + 2. * beta) * rho21;
+    const double Ymu = (4. + rho2 + 3. * beta * (1. + rho2)) /
+                       ((1. + rho2) * (1.5 + 2. * beta) * glibm::log(3. + xi, T.log_tab) + 1. -
+                        1.5 * rho2);
+    const double xmu = (1. + xi) * (1. + Ymu);
+    const double Lmu = glibm::log(p.p_raz13 * q / (p.p_z15 * (q + cLi * xmu)), T.log_tab);
+    double phi_mu = Bmu * Lmu;
+    if (phi_mu < 0.) phi_mu = 0.;
+    return -(phi_e + phi_mu / p.p_r2) * (1. - rho) * k.tmin;
+}
+
+// Atomic-electron form factor and normalisation (dcs.hh:229-257); `integral` is the 8-node sum
+NOA_HD double pair_finish(double K, double q, double integral, const PairKinematics &k,
+                          const Params &p, const glibm::Tables &T) {
+    const double gamma = k.gamma;
+    double zeta;
+    if (gamma <= 35.)
+        zeta = 0.;
+    else {
+        zeta = 0.073 * glibm::log(gamma / (1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T.log_tab) -
+               0.26;
+        if (zeta <= 0.)
+            zeta = 0.;
+        else
+            zeta /= 0.058 * glibm::log(gamma / (1. + p.p_g2 * gamma * p.p_z13), T.log_tab) - 0.14;
+    }
+    const double E = K + p.mass;
+    const double s = p.p_cz * (p.Zd + zeta) * (E - q) * integral / (q * E);
+    return (s < 0.) ? 0. : s * 1E+03 * kAvogadro * (p.mass + K) / p.A;
+}
+
+// One thread does all 8 nodes; accumulation order of numerics.hh:84-87 (h = 1, lb = 0)
+NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tables &T) {
+    PairKinematics k;
+    if (!pair_setup(K, q, p, T, k)) return 0.;
+    const double xs[8] = NOA_GL8_X;
+    const double ws[8] = NOA_GL8_W;
+    double acc = 0.;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) acc += pair_node(xs[j], q, k, p, T) * ws[j];
+    return pair_finish(K, q, acc, k, p, T);
+}
+
+// ------------------------------------------------------------------------------------------
+// Photonuclear -- src/noa/pms/dcs.hh:261-405
+// ------------------------------------------------------------------------------------------
+// ALLM97 F2 (dcs.hh:261-307)
+NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tables &T) {
+    const double m02 = 0.31985, mP2 = 49.457, mR2 = 0.15052, Q02 = 0.52544, Lambda2 = 0.06527;
+    const double cP1 = 0.28067, cP2 = 0.22291, cP3 = 2.1979;
+    const double aP1 = -0.0808, aP2 = -0.44812, aP3 = 1.1709;
+    const double bP1 = 0.36292, bP2 = 1.8917, bP3 = 1.8439;
+    const double cR1 = 0.80107, cR2 = 0.97307, cR3 = 3.4942;
+    const double aR1 = 0.58400, aR2 = 0.37888, aR3 = 2.6063;
+    const double bR1 = 0.01147, bR2 = 3.7582, bR3 = 0.49338;
+    const double M2 = 0.8803505929;
+
+    const double W2 = M2 + Q2 * (1.0 / x - 1.0);
+    const double t = glibm::log(glibm::log((Q2 + Q02) / Lambda2, T.log_tab) / p.n_logq0l,
+                                T.log_tab);
+    const double xP = (Q2 + mP2) / (Q2 + mP2 + W2 - M2);
+    const double xR = (Q2 + mR2) / (Q2 + mR2 + W2 - M2);
+    const double lnt = glibm::log(t, T.log_tab);
+    const double cP = cP1 + (cP1 - cP2) * (1.0 / (1.0 + glibm::exp(cP3 * lnt, T.exp_tab)) - 1.0);
+    const double aP = aP1 + (aP1 - aP2) * (1.0 / (1.0 + glibm::exp(aP3 * lnt, T.exp_tab)) - 1.0);
+    const double bP = bP1 + bP2 * glibm::exp(bP3 * lnt, T.exp_tab);
+    const double cR = cR1 + cR2 * glibm::exp(cR3 * lnt, T.exp_tab);
+    const double aR = aR1 + aR2 * glibm::exp(aR3 * lnt, T.exp_tab);
+    const double bR = bR1 + bR2 * glibm::exp(bR3 * lnt, T.exp_tab);
+
+    const double l1x = glibm::log(1 - x, T.log_tab);
+    const double F2P = cP * glibm::exp(aP * glibm::log(xP, T.log_tab) + bP * l1x, T.exp_tab);
+    const double F2R = cR * glibm::exp(aR * glibm::log(xR, T.log_tab) + bR * l1x, T.exp_tab);
+    return Q2 / (Q2 + m02) * (F2P + F2R);
+}
+
+// DRSS shadowing (dcs.hh:310-319)
+NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tables &T) {
+    double a = 1.0;
+    if (x < 0.0014)
+        a = p.n_alow;
+    else if (x < 0.04)
+        a = glibm::exp((0.069 * glibm::log10(x, T.log_tab) + 0.097) * p.n_logA, T.exp_tab);
+    return (p.n_halfA * a * (2.0 + x * (-1.85 + x * (2.45 + x * (-2.35 + x)))) * F2p);
+}
+
+// Whitlow R (dcs.hh:322-332)
+NOA_HD double r_whitlow(double x, double Q2, const glibm::Tables &T) {
+    double q2 = Q2;
+    if (Q2 < 0.3) q2 = 0.3;
+    const double theta = 1 + 12.0 * q2 / (1.0 + q2) * 0.015625 / (0.015625 + x * x);
+    return (0.635 / glibm::log(q2 / 0.04, T.log_tab) * theta + 0.5747 / q2 -
+            0.3534 / (0.09 + q2 * q2));
+}
+
+struct PhotoKinematics {   // per-(K,q) quantities of dcs.hh:372-387 and 340-342
+    double centre, width, E, y, Mq;
+};
+
+NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm::Tables &T,
+                               PhotoKinematics &k) {
+    if ((q < 1.) || (q < 2E-03 * K)) return false;            // dcs.hh:357-359
+    const double M = 0.931494;
+    const double mpi = 0.134977;
+    const double E = K + p.mass;
+    if ((q >= (E - p.mass)) || (q <= p.n_qpi)) return false;  // dcs.hh:374
+    const double y = q / E;
+    const double Q2min = p.n_m2 * y * y / (1 - y);
+    const double Q2max = 2.0 * M * (q - mpi) - mpi * mpi;
+    if ((Q2max < Q2min) | (Q2min < 0)) return false;
+    const double lo = glibm::log(Q2min, T.log_tab);
+    const double hi = glibm::log(Q2max, T.log_tab);
+    k.width = hi - lo;
+    k.centre = 0.5 * (hi + lo);
+    k.E = E;
+    k.y = y;
+    k.Mq = M * q;
+    return true;
+}
+
+// d2sigma/dq dQ2 * Q2 at node t in [-1,1] (dcs.hh:335-355, 397-402)
+NOA_HD double photonuclear_node(double t, double q, const PhotoKinematics &k, const Params &p,
+                                const glibm::Tables &T) {
+    const double cf = 2.603096E-35;
+    const double Q2 = glibm::exp(k.centre + 0.5 * k.width * t, T.exp_tab);
+    const double E = k.E;
+    const double y = k.y;
+    const double x = 0.5 * Q2 / k.Mq;
+    const double F2p = f2_allm(x, Q2, p, T);
+    const double F2A = f2a_drss(x, F2p, p, T);
+    const double R = r_whitlow(x, Q2, T);
+    const double dds =
+            (1 - y + 0.5 * (1 - p.n_2m2 / Q2) * (y * y + Q2 / (E * E)) / (1 + R)) / (Q2 * Q2) -
+            0.25 / (E * E * Q2);
+    return cf * F2A * dds / q * Q2;
+}
+
+NOA_HD double photonuclear_finish(double K, double ds, const PhotoKinematics &k, const Params &p) {
+    return (ds < 0.) ? 0. : 0.5 * ds * k.width * 1E+03 * kAvogadro * (p.mass + K) / p.A;
+}
+
+NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tables &T) {
+    PhotoKinematics k;
+    if (!photonuclear_setup(K, q, p, T, k)) return 0.;
+    const double xs[9] = NOA_GL9_X;
+    const double ws[9] = NOA_GL9_W;
+    double acc = 0.;
+#pragma unroll 1
+    for (int j = 0; j < 9; j++) acc += photonuclear_node(xs[j], q, k, p, T) * ws[j];
+    return photonuclear_finish(K, acc, k, p);
+}
+
+// ------------------------------------------------------------------------------------------
+// Ionisation -- src/noa/pms/dcs.hh:408-443
+// ------------------------------------------------------------------------------------------
+NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tables &T) {
+    const double me = kElectronMass;
+    const double P2 = K * (K + 2. * p.mass);
+    const double E = K + p.mass;
+    const double Wmax = 2. * me * P2 / (p.i_m2 + me * (me + 2. * E));
+    if ((Wmax < kXFraction * K) || (q > Wmax)) return 0.;
+    if (q <= p.i_wmin) return 0.;
+    const double a0 = 0.5 / P2;
+    const double a1 = -1. / Wmax;
+    const double a2 = E * E / P2;
+    const double cs = 1.535336E-05 * E * p.Zd / p.A * (a0 + 1. / q * (a1 + a2 / q));
+    double Delta = 0.;
+    if (K >= p.i_kthr) {
+        const double L1 = glibm::log(1. + 2. * q / me, T.log_tab);
+        Delta = 1.16141E-03 * L1 *
+                (glibm::log(4. * E * (E - q) / p.i_m2, T.log_tab) - L1);
+    }
+    return cs * (1. + Delta);
+}
+
+// Closed-form ionisation integrals (dcs.hh:446-496); integrand 0 = DEL, 1 = CEL
+NOA_HD double ionisation_closed_form(double K, double xlow, int integrand, const Params &p,
+                                     const glibm::Tables &T) {
+    const double me = kElectronMass;
+    const double P2 = K * (K + 2. * p.mass);
+    const double E = K + p.mass;
+    const double Wmax = 2. * me * P2 / (p.i_m2 + me * (me + 2. * E));
+    if (Wmax < kXFraction * K) return 0.;
+    double Wmin = p.i_wmin;
+    const double qlow = K * xlow;
+    if (qlow >= Wmin) Wmin = qlow;
+    if (Wmax <= Wmin) return 0.;
+    const double a0 = 0.5 / P2, a1 = -1. / Wmax, a2 = E * E / P2;
+    double term;
+    if (integrand == 0)
+        term = a0 * (Wmax - Wmin) + a1 * glibm::log(Wmax / Wmin, T.log_tab) +
+               a2 * (1. / Wmin - 1. / Wmax);
+    else
+        term = 0.5 * a0 * (Wmax * Wmax - Wmin * Wmin) + a1 * (Wmax - Wmin) +
+               a2 * glibm::log(Wmax / Wmin, T.log_tab);
+    return 1.535336E-05 * p.Zd / p.A * term;
+}
+
+template <int PROCESS>
+NOA_HD double dcs_eval(double K, double q, const Params &p, const glibm::Tables &T) {
+    if (PROCESS == 0) return bremsstrahlung(K, q, p, T);
+    if (PROCESS == 1) return pair_production(K, q, p, T);
+    if (PROCESS == 2) return photonuclear(K, q, p, T);
+    return ionisation(K, q, p, T);
+}
+
+}  // namespace noa_b200

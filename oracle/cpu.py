@@ -1,0 +1,109 @@
+"""ctypes bindings for the two CPU checkers (test infrastructure, see oracle/__init__.py)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(_HERE, "_build", "libdcs_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libnoa_ref.so")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+PROCESSES = ("bremsstrahlung", "pair_production", "photonuclear", "ionisation")
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+
+
+class Checker:
+    """Uniform face over the C port and the compiled reference.
+
+    vmap(process, K, q, element, mass, threads)            -> dcs::vmap / dcs::pvmap
+    vmap_integral(process, integrand, K, xlow, n, el, m)   -> dcs::vmap_integral(recoil_integral)
+    `element` is (A [g/mol], I [GeV], Z); `integrand` 0 = del (dcs*q), 1 = cel (dcs*q*q).
+    """
+
+    def __init__(self, lib, kind):
+        self.kind = kind  # "port" | "reference"
+        self._lib = lib
+        pre = "oracle_" if kind == "port" else "noa_ref_"
+        self._vmap = getattr(lib, pre + "vmap")
+        self._vint = getattr(lib, pre + "vmap_integral")
+        self._vmap.restype = ctypes.c_int
+        self._vint.restype = ctypes.c_int
+        self._vmap.argtypes = [ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int64,
+                               ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_double]
+        self._vint.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int64,
+                               ctypes.c_double, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
+                               ctypes.c_int32, ctypes.c_double]
+        thr = getattr(lib, "oracle_max_threads" if kind == "port" else "noa_ref_threads")
+        thr.restype = ctypes.c_int
+        self.max_threads = int(thr())
+
+    def _threads_arg(self, threads):
+        # the port takes a thread count, the reference shim a serial/OpenMP switch
+        # (OpenMP team size of the reference = OMP_NUM_THREADS / all cores)
+        if self.kind == "port":
+            return int(threads)
+        return 1 if threads > 1 else 0
+
+    def vmap(self, process, K, q, element, mass, threads=1):
+        K, q = _f64(K), _f64(q)
+        assert K.size == q.size
+        out = np.zeros_like(K)
+        rc = self._vmap(int(process), self._threads_arg(threads), _p(K), _p(q), _p(out), K.size,
+                        float(element[0]), float(element[1]), int(element[2]), float(mass))
+        if rc:
+            raise ValueError(f"bad process {process}")
+        return out
+
+    def vmap_integral(self, process, integrand, K, xlow, min_points, element, mass, threads=1):
+        K = _f64(K)
+        out = np.zeros_like(K)
+        rc = self._vint(int(process), int(integrand), self._threads_arg(threads), _p(K), _p(out),
+                        K.size, float(xlow), int(min_points), float(element[0]),
+                        float(element[1]), int(element[2]), float(mass))
+        if rc:
+            raise ValueError(f"bad process {process}")
+        return out
+
+
+def _make(target):
+    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
+
+
+def build_port():
+    _make("oracle")
+    return PORT_SO
+
+
+def build_reference(reference_root="/root/reference"):
+    """Compile the unmodified reference where it lies; returns None when it is not present."""
+    if not os.path.isdir(os.path.join(reference_root, "src", "noa")):
+        return REF_SO if os.path.exists(REF_SO) else None
+    _make("ref")
+    return REF_SO
+
+
+def load_port():
+    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(
+            os.path.join(_HERE, "dcs_oracle.c")):
+        build_port()
+    return Checker(ctypes.CDLL(PORT_SO), "port")
+
+
+def load_reference():
+    """The compiled reference, or None if oracle/_ref was never built (it cannot be built on a
+    box without /root/reference; the prebuilt .so travels there with gpurun)."""
+    if not os.path.exists(REF_SO):
+        return None
+    try:
+        return Checker(ctypes.CDLL(REF_SO), "reference")
+    except OSError:
+        return None

@@ -1,0 +1,91 @@
+// TEST INFRASTRUCTURE ONLY -- never linked or imported by the product path (noa_b200/).
+//
+// C-ABI shim around the UNMODIFIED reference headers, compiled where they lie under
+// /root/reference/src (recipe: oracle/Makefile, output: oracle/_ref/libnoa_ref.so, git-ignored).
+// It lets the tests / bench.py cpu_baseline call the reference's own CPU implementation of the
+// DCS hot path on raw double buffers:
+//   noa::pms::dcs::vmap / pvmap           (src/noa/pms/dcs.hh:35-75)
+//   noa::pms::dcs::vmap_integral          (src/noa/pms/dcs.hh:115-130)
+//   noa::pms::dcs::recoil_integral        (src/noa/pms/dcs.hh:89-105, 955-1001)
+// No reference source is copied into this repository; this file only *calls* it.
+#include <noa/pms/dcs.hh>
+
+#include <omp.h>
+#include <cstdint>
+
+using namespace noa::pms;
+
+namespace {
+    inline torch::Tensor wrap(const double *p, int64_t n) {
+        return torch::from_blob(const_cast<double *>(p), {n}, torch::kFloat64);
+    }
+
+    template<typename F>
+    inline void run_vmap(const F &f, int parallel, double *out, const double *K, const double *q,
+                         int64_t n, const AtomicElement &el, double mass) {
+        auto r = wrap(out, n);
+        auto k = wrap(K, n);
+        auto qq = wrap(q, n);
+        if (parallel) dcs::pvmap(f)(r, k, qq, el, mass);
+        else dcs::vmap(f)(r, k, qq, el, mass);
+    }
+
+    template<typename F, typename G>
+    inline void run_integral(const F &f, const G &g, int parallel, double *out, const double *K,
+                             int64_t n, double xlow, const AtomicElement &el, double mass,
+                             int32_t min_points) {
+        if (!parallel) {
+            // the reference's own (serial-only) driver
+            auto r = wrap(out, n);
+            auto k = wrap(K, n);
+            dcs::vmap_integral(dcs::recoil_integral(f, g))(r, k, xlow, el, mass, min_points);
+        } else {
+            // harness-side OpenMP loop over energies around the unmodified closure
+            // ("harness-parallelised reference arithmetic")
+#pragma omp parallel for schedule(dynamic, 8)
+            for (int64_t i = 0; i < n; i++)
+                out[i] = dcs::recoil_integral(f, g)(K[i], xlow, el, mass, min_points);
+        }
+    }
+}
+
+extern "C" {
+
+int noa_ref_threads() { return omp_get_max_threads(); }
+
+// process: 0 brems, 1 pair, 2 photonuclear, 3 ionisation
+int noa_ref_vmap(int process, int parallel, const double *K, const double *q, double *out,
+                 int64_t n, double A, double I, int32_t Z, double mass) {
+    const AtomicElement el{A, I, Z};
+    switch (process) {
+        case 0: run_vmap(dcs::bremsstrahlung, parallel, out, K, q, n, el, mass); return 0;
+        case 1: run_vmap(dcs::pair_production, parallel, out, K, q, n, el, mass); return 0;
+        case 2: run_vmap(dcs::photonuclear, parallel, out, K, q, n, el, mass); return 0;
+        case 3: run_vmap(dcs::ionisation, parallel, out, K, q, n, el, mass); return 0;
+    }
+    return 1;
+}
+
+// integrand: 0 = del_integrand (dcs*q), 1 = cel_integrand (dcs*q*q)
+int noa_ref_vmap_integral(int process, int integrand, int parallel, const double *K, double *out,
+                          int64_t n, double xlow, int32_t min_points, double A, double I,
+                          int32_t Z, double mass) {
+    const AtomicElement el{A, I, Z};
+#define NOA_REF_CASE(P, F)                                                                       \
+    case P:                                                                                      \
+        if (integrand == 0)                                                                      \
+            run_integral(F, dcs::del_integrand, parallel, out, K, n, xlow, el, mass, min_points); \
+        else                                                                                     \
+            run_integral(F, dcs::cel_integrand, parallel, out, K, n, xlow, el, mass, min_points); \
+        return 0;
+    switch (process) {
+        NOA_REF_CASE(0, dcs::bremsstrahlung)
+        NOA_REF_CASE(1, dcs::pair_production)
+        NOA_REF_CASE(2, dcs::photonuclear)
+        NOA_REF_CASE(3, dcs::ionisation)
+    }
+#undef NOA_REF_CASE
+    return 1;
+}
+
+}  // extern "C"
