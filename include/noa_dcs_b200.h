@@ -1,0 +1,140 @@
+/*
+ * noa_dcs_b200 -- C ABI of the B200-native muon DCS hot path (libnoa_dcs_b200.so).
+ *
+ * Plain pointers and sizes, no torch types.  Every device entry point is asynchronous on the
+ * CUDA stream it is given (a `cudaStream_t` passed as `void *`; NULL = the legacy default stream,
+ * which is what the reference launches on, src/noa/utils/common.cuh:55), never allocates or frees
+ * caller memory, performs no hidden synchronisation and is re-entrant.  All arrays are contiguous
+ * FP64.  Return value: 0 on success, a positive `cudaError_t`, or a negative NOA_DCS_E* code;
+ * noa_dcs_strerror() explains either.
+ *
+ * Reference interfaces these entry points replace (paths relative to the reference tree):
+ *   noa_dcs_vmap_f64           dcs::cuda::vmap_bremsstrahlung       src/noa/pms/dcs.hh:1006-1011,
+ *                                                                   src/noa/pms/dcs.cuh:30-41
+ *                              and, on the GPU, dcs::vmap(f) / dcs::pvmap(f) for
+ *                              f = bremsstrahlung | pair_production | photonuclear | ionisation
+ *                                                                   src/noa/pms/dcs.hh:35-75
+ *   noa_dcs_vmap_all_f64       the four dcs::vmap(f) calls of docs/pms/muon_dcs.cc:8-27 fused
+ *   noa_dcs_vmap_mixture_f64   per-element DCS mixed by mass fraction (a "material"; the
+ *                              reference has single elements only, src/noa/pms/physics.hh:39-43)
+ *   noa_dcs_vmap_integral_f64  dcs::vmap_integral(dcs::recoil_integral(f, del|cel_integrand))
+ *                                                                   src/noa/pms/dcs.hh:89-130,
+ *                                                                   955-1001
+ *   noa_dcs_table_f64          the eight such columns (4 processes x DEL, CEL) of one element in
+ *                              one launch, one DCS evaluation per node feeding both integrands
+ *   noa_dcs_vmap_host_f64      dcs::map(f) on CPU tensors           src/noa/pms/dcs.hh:50-60
+ *                              (host buffers in, host buffers out; copies pipelined with compute)
+ */
+#ifndef NOA_DCS_B200_H
+#define NOA_DCS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOA_DCS_ABI_VERSION 1
+
+/* process ids: PUMAS / NOA order (NPR = 4, src/noa/pms/physics.hh:86) */
+#define NOA_DCS_BREMSSTRAHLUNG 0
+#define NOA_DCS_PAIR_PRODUCTION 1
+#define NOA_DCS_PHOTONUCLEAR 2
+#define NOA_DCS_IONISATION 3
+#define NOA_DCS_NPROCESS 4
+
+#define NOA_DCS_MAX_ELEMENTS 8 /* elements per material in noa_dcs_vmap_mixture_f64 */
+
+/* negative error codes (positive ones are cudaError_t) */
+#define NOA_DCS_EINVAL (-1)  /* bad process id / mask / count / null pointer */
+#define NOA_DCS_ERANGE (-2)  /* size out of the supported range */
+#define NOA_DCS_ENODEV (-3)  /* no CUDA device: there is no CPU fallback */
+
+int noa_dcs_abi_version(void);
+const char *noa_dcs_strerror(int code);
+
+/* Number of CUDA devices visible; <= 0 means the library cannot run (no CPU path exists). */
+int noa_dcs_device_count(void);
+
+/*
+ * result[i] = f_process(K[i], q[i], element, mass), i in [0, n).   K, q, result: device pointers.
+ * Same semantics as the reference's scalar functions: values outside the kinematic range give
+ * exactly 0, NaNs propagate, bremsstrahlung has no range guard (src/noa/pms/physics.hh:135-152).
+ */
+int noa_dcs_vmap_f64(int process, const double *K, const double *q, double *result, int64_t n,
+                     double A, double I, int32_t Z, double mass, void *stream);
+
+/* result[p * n + i] for the four processes p (one pass over K, q). */
+int noa_dcs_vmap_all_f64(const double *K, const double *q, double *result, int64_t n, double A,
+                         double I, int32_t Z, double mass, void *stream);
+
+/*
+ * Material DCS: for every process p in process_mask (bit p set), in increasing p, slot s = rank of
+ * p within the mask:
+ *   result[s * n + i] = sum_e w[e] * f_p(K[i], q[i], element e, mass)      (e = 0 .. n_elements-1,
+ * accumulated in that order starting from 0).   A, I, Z, w are HOST arrays of n_elements entries.
+ */
+int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const double *q,
+                             double *result, int64_t n, int32_t n_elements, const double *A,
+                             const double *I, const int32_t *Z, const double *w, double mass,
+                             void *stream);
+
+/*
+ * Energy-loss tables.  For every process p in process_mask and every energy K[i]:
+ *   del[p * nK + i] = recoil_integral(f_p, del_integrand)(K[i], xlow, element, mass, min_points)
+ *   cel[p * nK + i] = recoil_integral(f_p, cel_integrand)(K[i], xlow, element, mass, min_points)
+ * i.e. composite 6-point Gauss-Legendre in ln q over [ln(K xlow), ln K] with
+ * ceil(min_points / 6) cells, nodes accumulated in the reference's serial order, divided by
+ * (K + mass); ionisation uses the closed form for K <= 0.5 (m - me)^2 / me.
+ * del / cel are device arrays of 4 * nK doubles; rows of processes not in the mask are untouched.
+ * Either may be NULL to skip that integrand.
+ */
+int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                      int32_t min_points, double A, double I, int32_t Z, double mass, double *del,
+                      double *cel, void *stream);
+
+/*
+ * One column of the above, with the reference's own call shape
+ *   dcs::vmap_integral(dcs::recoil_integral(f_process, integrand))(result, K, xlow, element, mass,
+ *                                                                  min_points)
+ * (src/noa/pms/dcs.hh:115-130).  integrand: 0 = del_integrand (dcs * q), 1 = cel_integrand
+ * (dcs * q * q), src/noa/pms/dcs.hh:107-113.  result: n doubles on the device.
+ */
+int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, double *result,
+                              int64_t n, double xlow, int32_t min_points, double A, double I,
+                              int32_t Z, double mass, void *stream);
+
+/*
+ * Host-buffer form of noa_dcs_vmap_f64 (process 0..3) and noa_dcs_vmap_all_f64 (process = 4,
+ * h_result holds 4 * n doubles): copies h_K, h_q to the device in chunks, evaluates, copies the
+ * result back, the three stages overlapped on separate streams.  Blocks until h_result is
+ * complete.  Pinned (page-locked) host buffers give full PCIe speed; pageable ones still work.
+ * The stager owns the device scratch and streams so repeated calls do not allocate.
+ */
+typedef struct noa_dcs_stager noa_dcs_stager;
+int noa_dcs_stager_create(noa_dcs_stager **out, int64_t chunk_pairs, int32_t n_slots);
+int noa_dcs_stager_destroy(noa_dcs_stager *stager);
+int noa_dcs_vmap_host_f64(noa_dcs_stager *stager, int process, const double *h_K,
+                          const double *h_q, double *h_result, int64_t n, double A, double I,
+                          int32_t Z, double mass);
+
+/*
+ * Measurement helpers (bench.py): a dependent-chain-free DFMA loop used to measure the FP64-pipe
+ * peak that the rooflines are quoted against.  Executes blocks * threads * iters * 16 DFMA.
+ */
+int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink, void *stream);
+
+/* Lane mapping of the pair-production kernel: 0 = one pair per thread (default), 1 = one
+ * Gauss-Legendre node per lane (8 lanes per pair, shuffle gather).  Same results either way. */
+int noa_dcs_set_pair_mode(int mode);
+
+/* Launch geometry the element-wise kernels use on the current device (for reporting). */
+int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t *sm_count);
+
+/* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
+int64_t noa_dcs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOA_DCS_B200_H */

@@ -1,0 +1,594 @@
+// B200 (sm_100a) kernels of the muon DCS hot path and the C ABI that exposes them
+// (include/noa_dcs_b200.h).  Torch-free on purpose: this file compiles in seconds and is the
+// whole product below the LibTorch boundary.
+//
+// Kernels
+//   vmap_kernel<P, VEC>     element-wise DCS of one process, one (K, q) pair per thread and
+//                           iteration, persistent grid-stride blocks, 128-bit loads/stores
+//   vmap_pair_lanes_kernel  pair production with one Gauss-Legendre node per lane (8 lanes per
+//                           pair, shuffle gather, serial-order sum) -- kept for the measured
+//                           comparison in DESIGN.md
+//   vmap_all_kernel         the four processes of one pair in one pass (16 B in, 32 B out)
+//   vmap_mixture_kernel     sum_e w_e * DCS_e for the processes of a mask (water = H + O)
+//   table_kernel            one CTA per (process, energy) row of the DEL/CEL tables: nodes of the
+//                           composite 6-point rule across threads, node terms staged in shared
+//                           memory and accumulated in the reference's serial order
+//   fp64_probe_kernel       dependent-chain-free DFMA loop (roofline denominator)
+//
+// Numerics: FP64 throughout, every operation IEEE (see dcs_math.cuh, glibm.cuh); this file must be
+// compiled with -fmad=false.  The exp/log tables (4 KB) are staged into shared memory per CTA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <new>
+
+#include "../../include/noa_dcs_b200.h"
+#include "dcs_math.cuh"
+#include "dcs_params.hh"
+
+namespace noa_b200 {
+
+__device__ const glibm::Tables g_tables = {GLIBM_EXP_TABLE_INIT, GLIBM_LOG_TABLE_INIT};
+
+constexpr int kThreads = 256;
+
+// 4 KB global -> shared, coalesced 128-bit copies
+__device__ __forceinline__ void stage_tables(glibm::Tables &dst) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
+    uint4 *d = reinterpret_cast<uint4 *>(&dst);
+    for (int i = threadIdx.x; i < (int) (sizeof(glibm::Tables) / sizeof(uint4)); i += blockDim.x)
+        d[i] = src[i];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise, one process
+// ------------------------------------------------------------------------------------------
+template <int PROCESS, int VEC>
+__global__ void __launch_bounds__(kThreads)
+vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *__restrict__ out,
+            int64_t n, const __grid_constant__ Params p) {
+    __shared__ glibm::Tables T;
+    stage_tables(T);
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC == 2) {
+        const int64_t n2 = n >> 1;
+        const double2 *K2 = reinterpret_cast<const double2 *>(K);
+        const double2 *q2 = reinterpret_cast<const double2 *>(q);
+        double2 *o2 = reinterpret_cast<double2 *>(out);
+        for (int64_t i = tid; i < n2; i += stride) {
+            const double2 k = K2[i];
+            const double2 r = q2[i];
+            double2 o;
+            o.x = dcs_eval<PROCESS>(k.x, r.x, p, T);
+            o.y = dcs_eval<PROCESS>(k.y, r.y, p, T);
+            o2[i] = o;
+        }
+        if (tid == 0 && (n & 1)) out[n - 1] = dcs_eval<PROCESS>(K[n - 1], q[n - 1], p, T);
+    } else {
+        for (int64_t i = tid; i < n; i += stride) out[i] = dcs_eval<PROCESS>(K[i], q[i], p, T);
+    }
+}
+
+// pair production, one quadrature node per lane: lanes 8g..8g+7 of a warp share pair g.
+__global__ void __launch_bounds__(kThreads)
+vmap_pair_lanes_kernel(const double *__restrict__ K, const double *__restrict__ q,
+                       double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
+    __shared__ glibm::Tables T;
+    stage_tables(T);
+    const int lane = threadIdx.x & 31;
+    const int node = lane & 7;
+    const int64_t groups = ((int64_t) gridDim.x * blockDim.x) >> 3;
+    const int64_t g0 = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t rounds = (n + groups - 1) / groups;     // uniform trip count: shuffles are warp-wide
+    for (int64_t it = 0; it < rounds; it++) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        const double k = live ? K[i] : 1.0;
+        const double r = live ? q[i] : 1.0;
+        PairKinematics kin;
+        const bool inside = live && pair_setup(k, r, p, T, kin);
+        double term = 0.;
+        if (inside) term = pair_node(c_gl8_x[node], r, kin, p, T) * c_gl8_w[node];
+        // gather the 8 node terms of the group and add them in node order (numerics.hh:84-87)
+        double acc = 0.;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += __shfl_sync(0xffffffffu, term, (lane & 24) | j);
+        if (live && node == 0) out[i] = inside ? pair_finish(k, r, acc, kin, p, T) : 0.;
+    }
+}
+
+// element-wise, all four processes of a pair: out[p * n + i]
+__global__ void __launch_bounds__(kThreads)
+vmap_all_kernel(const double *__restrict__ K, const double *__restrict__ q,
+                double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
+    __shared__ glibm::Tables T;
+    stage_tables(T);
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double k = K[i], r = q[i];
+        out[i] = bremsstrahlung(k, r, p, T);
+        out[n + i] = pair_production(k, r, p, T);
+        out[2 * n + i] = photonuclear(k, r, p, T);
+        out[3 * n + i] = ionisation(k, r, p, T);
+    }
+}
+
+struct Mixture {
+    int32_t n_elements;
+    uint32_t process_mask;
+    double w[NOA_DCS_MAX_ELEMENTS];
+    Params p[NOA_DCS_MAX_ELEMENTS];
+};
+
+__device__ __forceinline__ double dcs_dispatch(int process, double k, double r, const Params &p,
+                                               const glibm::Tables &T) {
+    switch (process) {
+        case 0: return bremsstrahlung(k, r, p, T);
+        case 1: return pair_production(k, r, p, T);
+        case 2: return photonuclear(k, r, p, T);
+        default: return ionisation(k, r, p, T);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
+                    double *__restrict__ out, int64_t n, const __grid_constant__ Mixture m) {
+    __shared__ glibm::Tables T;
+    stage_tables(T);
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double k = K[i], r = q[i];
+        int slot = 0;
+#pragma unroll 1
+        for (int process = 0; process < NOA_DCS_NPROCESS; process++) {
+            if (!((m.process_mask >> process) & 1u)) continue;
+            double acc = 0.;
+#pragma unroll 1
+            for (int e = 0; e < m.n_elements; e++)
+                acc += m.w[e] * dcs_dispatch(process, k, r, m.p[e], T);
+            out[(int64_t) slot * n + i] = acc;
+            slot++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// energy-loss tables: dcs::vmap_integral(dcs::recoil_integral(f, del|cel_integrand))
+// (src/noa/pms/dcs.hh:89-130, 955-1001; src/noa/utils/numerics.hh:72-108)
+// ------------------------------------------------------------------------------------------
+constexpr int kTableChunk = 1536;   // node terms staged per pass: 2 x 12 KB of shared memory
+
+struct TablePlan {
+    int32_t n_slots;          // processes to build
+    int32_t process[4];       // heaviest first, so the tail of the grid is cheap rows
+    int32_t out_row[4];       // output row of process p (p for full tables, 0 for a single column)
+    uint32_t cells;           // ceil(min_points / 6)
+    double xlow;
+};
+
+__global__ void __launch_bounds__(kThreads)
+table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
+             double *__restrict__ cel, const __grid_constant__ TablePlan plan,
+             const __grid_constant__ Params p) {
+    __shared__ glibm::Tables T;
+    __shared__ double s_del[kTableChunk];
+    __shared__ double s_cel[kTableChunk];
+    stage_tables(T);
+
+    const int64_t b = blockIdx.x;
+    const int process = plan.process[b / nK];
+    const int64_t row = nK - 1 - (b % nK);
+    const double k = K[row];
+    const int tid = threadIdx.x;
+
+    if (process == 3 && k <= p.i_kthr) {          // dcs.hh:963-966, 987-990
+        const int64_t at = (int64_t) plan.out_row[3] * nK + row;
+        if (tid == 0 && del) del[at] = ionisation_closed_form(k, plan.xlow, 0, p, T);
+        if (tid == 32 && cel) cel[at] = ionisation_closed_form(k, plan.xlow, 1, p, T);
+        return;
+    }
+
+    const double lb = glibm::log(k * plan.xlow, T.log_tab);
+    const double ub = glibm::log(k, T.log_tab);
+    const double h = (ub - lb) / plan.cells;
+    const uint32_t total = plan.cells * 6u;
+    double acc = 0.;
+    for (uint32_t base = 0; base < total; base += kTableChunk) {
+        const uint32_t count = min((uint32_t) kTableChunk, total - base);
+        for (uint32_t i = base + tid; i < base + count; i += kThreads) {
+            const uint32_t j = i % 6u;
+            const double x = lb + h * ((i / 6u) + c_gl6_x[j]);
+            const double r = glibm::exp(x, T.exp_tab);
+            const double f = dcs_dispatch(process, k, r, p, T);
+            const double w = c_gl6_w[j];
+            const double fr = f * r;
+            s_del[i - base] = fr * h * w;           // del_integrand, dcs.hh:107-109
+            s_cel[i - base] = fr * r * h * w;       // cel_integrand, dcs.hh:111-113
+        }
+        __syncthreads();
+        // res += term, strictly in node order (numerics.hh:84-87): one lane per integrand
+        if (tid == 0) {
+            for (uint32_t i = 0; i < count; i++) acc += s_del[i];
+        } else if (tid == 32) {
+            for (uint32_t i = 0; i < count; i++) acc += s_cel[i];
+        }
+        __syncthreads();
+    }
+    const int64_t at = (int64_t) plan.out_row[process] * nK + row;
+    if (tid == 0 && del) del[at] = acc / (k + p.mass);
+    if (tid == 32 && cel) cel[at] = acc / (k + p.mass);
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 peak probe: 16 independent DFMA chains per thread
+// ------------------------------------------------------------------------------------------
+__global__ void fp64_probe_kernel(int64_t iters, double *sink) {
+    double a[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+    const double b = 0.999999, c = 1e-6;
+    for (int64_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = fma(a[j], b, c);
+    }
+    double s = 0.;
+#pragma unroll
+    for (int j = 0; j < 16; j++) s += a[j];
+    if (s == 123456.789) sink[0] = s;   // never true; keeps the chains alive
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_launches{0};
+
+struct DeviceInfo {
+    int sm_count = 0;
+    bool ok = false;
+};
+
+static int device_info(DeviceInfo &info) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+                                         ? NOA_DCS_ENODEV
+                                         : (int) e;
+    static std::mutex mu;
+    static int cached_sm[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 64 && cached_sm[dev]) {
+        info.sm_count = cached_sm[dev];
+        info.ok = true;
+        return 0;
+    }
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int) e;
+    if (dev < 64) cached_sm[dev] = sms;
+    info.sm_count = sms;
+    info.ok = true;
+    return 0;
+}
+
+template <typename Kernel>
+static int persistent_grid(Kernel kernel, int64_t work_items, int &blocks) {
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (e != cudaSuccess) return (int) e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (work_items + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t) info.sm_count * per_sm;
+    blocks = (int) (need < cap ? need : cap);
+    if (blocks < 1) blocks = 1;
+    return 0;
+}
+
+static inline int after_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int) cudaPeekAtLastError();
+}
+
+static inline bool aligned16(const void *a, const void *b, const void *c) {
+    return ((((uintptr_t) a) | ((uintptr_t) b) | ((uintptr_t) c)) & 15u) == 0;
+}
+
+template <int PROCESS>
+static int launch_vmap(const double *K, const double *q, double *out, int64_t n, const Params &p,
+                       cudaStream_t s) {
+    int blocks = 0;
+    // 128-bit loads/stores pay for the two streaming processes; the quadrature-bound ones keep
+    // one pair per thread so the (large) integrand is instantiated once
+    constexpr bool kStreaming = (PROCESS == 0 || PROCESS == 3);
+    if (kStreaming && aligned16(K, q, out) && n >= 2) {
+        int rc = persistent_grid(vmap_kernel<PROCESS, 2>, n >> 1, blocks);
+        if (rc) return rc;
+        vmap_kernel<PROCESS, 2><<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
+    } else {
+        int rc = persistent_grid(vmap_kernel<PROCESS, 1>, n, blocks);
+        if (rc) return rc;
+        vmap_kernel<PROCESS, 1><<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
+    }
+    return after_launch();
+}
+
+static int g_pair_mode = 0;   // 0: one pair per thread (default), 1: one node per lane
+
+static int vmap_impl(int process, const double *K, const double *q, double *out, int64_t n,
+                     const Params &p, cudaStream_t s) {
+    switch (process) {
+        case NOA_DCS_BREMSSTRAHLUNG: return launch_vmap<0>(K, q, out, n, p, s);
+        case NOA_DCS_PAIR_PRODUCTION:
+            if (g_pair_mode == 1) {
+                int blocks = 0;
+                int rc = persistent_grid(vmap_pair_lanes_kernel, n * 8, blocks);
+                if (rc) return rc;
+                vmap_pair_lanes_kernel<<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
+                return after_launch();
+            }
+            return launch_vmap<1>(K, q, out, n, p, s);
+        case NOA_DCS_PHOTONUCLEAR: return launch_vmap<2>(K, q, out, n, p, s);
+        case NOA_DCS_IONISATION: return launch_vmap<3>(K, q, out, n, p, s);
+    }
+    return NOA_DCS_EINVAL;
+}
+
+static int vmap_all_impl(const double *K, const double *q, double *out, int64_t n, const Params &p,
+                         cudaStream_t s) {
+    int blocks = 0;
+    int rc = persistent_grid(vmap_all_kernel, n, blocks);
+    if (rc) return rc;
+    vmap_all_kernel<<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
+    return after_launch();
+}
+
+}  // namespace noa_b200
+
+using namespace noa_b200;
+
+// staging object of noa_dcs_vmap_host_f64
+struct noa_dcs_stager {
+    int64_t chunk = 0;
+    int32_t n_slots = 0;
+    cudaStream_t *streams = nullptr;
+    double **dK = nullptr, **dq = nullptr, **dout = nullptr;   // per slot; dout holds 4 * chunk
+};
+
+extern "C" {
+
+int noa_dcs_abi_version(void) { return NOA_DCS_ABI_VERSION; }
+
+const char *noa_dcs_strerror(int code) {
+    switch (code) {
+        case 0: return "success";
+        case NOA_DCS_EINVAL: return "noa_dcs: invalid argument";
+        case NOA_DCS_ERANGE: return "noa_dcs: size out of range";
+        case NOA_DCS_ENODEV: return "noa_dcs: no CUDA device (this library has no CPU path)";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t) code);
+    return "noa_dcs: unknown error";
+}
+
+int noa_dcs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void) cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t noa_dcs_launch_count(void) { return g_launches.load(); }
+
+// test/bench hook: 0 = pair per thread, 1 = node per lane.  Not part of the reference surface.
+int noa_dcs_set_pair_mode(int mode) {
+    if (mode != 0 && mode != 1) return NOA_DCS_EINVAL;
+    g_pair_mode = mode;
+    return 0;
+}
+
+int noa_dcs_vmap_f64(int process, const double *K, const double *q, double *result, int64_t n,
+                     double A, double I, int32_t Z, double mass, void *stream) {
+    if (process < 0 || process >= NOA_DCS_NPROCESS || n < 0) return NOA_DCS_EINVAL;
+    if (n == 0) return 0;
+    if (!K || !q || !result) return NOA_DCS_EINVAL;
+    const Params p = make_params(A, I, Z, mass);
+    return vmap_impl(process, K, q, result, n, p, (cudaStream_t) stream);
+}
+
+int noa_dcs_vmap_all_f64(const double *K, const double *q, double *result, int64_t n, double A,
+                         double I, int32_t Z, double mass, void *stream) {
+    if (n < 0) return NOA_DCS_EINVAL;
+    if (n == 0) return 0;
+    if (!K || !q || !result) return NOA_DCS_EINVAL;
+    const Params p = make_params(A, I, Z, mass);
+    return vmap_all_impl(K, q, result, n, p, (cudaStream_t) stream);
+}
+
+int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const double *q,
+                             double *result, int64_t n, int32_t n_elements, const double *A,
+                             const double *I, const int32_t *Z, const double *w, double mass,
+                             void *stream) {
+    if (n < 0 || n_elements < 1 || n_elements > NOA_DCS_MAX_ELEMENTS) return NOA_DCS_EINVAL;
+    if (process_mask == 0 || process_mask > 15u || !A || !I || !Z || !w) return NOA_DCS_EINVAL;
+    if (n == 0) return 0;
+    if (!K || !q || !result) return NOA_DCS_EINVAL;
+    Mixture m{};
+    m.n_elements = n_elements;
+    m.process_mask = process_mask;
+    for (int e = 0; e < n_elements; e++) {
+        m.w[e] = w[e];
+        m.p[e] = make_params(A[e], I[e], Z[e], mass);
+    }
+    int blocks = 0;
+    int rc = persistent_grid(vmap_mixture_kernel, n, blocks);
+    if (rc) return rc;
+    vmap_mixture_kernel<<<blocks, kThreads, 0, (cudaStream_t) stream>>>(K, q, result, n, m);
+    return after_launch();
+}
+
+static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
+                      double xlow, int32_t min_points, double A, double I, int32_t Z, double mass,
+                      double *del, double *cel, void *stream) {
+    if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1)
+        return NOA_DCS_EINVAL;
+    if (nK == 0 || (!del && !cel)) return 0;
+    if (!K) return NOA_DCS_EINVAL;
+    TablePlan plan{};
+    for (int i = 0; i < 4; i++) plan.out_row[i] = single_row ? 0 : i;
+    static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
+                                       NOA_DCS_BREMSSTRAHLUNG, NOA_DCS_IONISATION};
+    for (int i = 0; i < 4; i++)
+        if ((process_mask >> heavy_first[i]) & 1u) plan.process[plan.n_slots++] = heavy_first[i];
+    plan.cells = ((uint32_t) min_points + 5u) / 6u;
+    plan.xlow = xlow;
+    const int64_t blocks = nK * plan.n_slots;
+    if (blocks > 0x7fffffffLL) return NOA_DCS_ERANGE;
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const Params p = make_params(A, I, Z, mass);
+    table_kernel<<<(unsigned) blocks, kThreads, 0, (cudaStream_t) stream>>>(K, nK, del, cel, plan,
+                                                                           p);
+    return after_launch();
+}
+
+int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                      int32_t min_points, double A, double I, int32_t Z, double mass, double *del,
+                      double *cel, void *stream) {
+    return table_impl(process_mask, false, K, nK, xlow, min_points, A, I, Z, mass, del, cel,
+                      stream);
+}
+
+int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, double *result,
+                              int64_t n, double xlow, int32_t min_points, double A, double I,
+                              int32_t Z, double mass, void *stream) {
+    if (process < 0 || process >= NOA_DCS_NPROCESS || (integrand != 0 && integrand != 1))
+        return NOA_DCS_EINVAL;
+    if (n > 0 && !result) return NOA_DCS_EINVAL;
+    return table_impl(1u << process, true, K, n, xlow, min_points, A, I, Z, mass,
+                      integrand == 0 ? result : nullptr, integrand == 1 ? result : nullptr, stream);
+}
+
+int noa_dcs_stager_create(noa_dcs_stager **out, int64_t chunk_pairs, int32_t n_slots) {
+    if (!out || chunk_pairs < 1 || n_slots < 1 || n_slots > 16) return NOA_DCS_EINVAL;
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    noa_dcs_stager *st = new (std::nothrow) noa_dcs_stager();
+    if (!st) return (int) cudaErrorMemoryAllocation;
+    st->chunk = chunk_pairs;
+    st->n_slots = n_slots;
+    st->streams = new cudaStream_t[n_slots]();
+    st->dK = new double *[n_slots]();
+    st->dq = new double *[n_slots]();
+    st->dout = new double *[n_slots]();
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < n_slots && e == cudaSuccess; s++) {
+        e = cudaStreamCreateWithFlags(&st->streams[s], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&st->dK[s], chunk_pairs * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&st->dq[s], chunk_pairs * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&st->dout[s], 4 * chunk_pairs * sizeof(double));
+    }
+    if (e != cudaSuccess) {
+        noa_dcs_stager_destroy(st);
+        return (int) e;
+    }
+    *out = st;
+    return 0;
+}
+
+int noa_dcs_stager_destroy(noa_dcs_stager *st) {
+    if (!st) return 0;
+    for (int s = 0; s < st->n_slots; s++) {
+        if (st->streams && st->streams[s]) {
+            cudaStreamSynchronize(st->streams[s]);
+            cudaStreamDestroy(st->streams[s]);
+        }
+        if (st->dK && st->dK[s]) cudaFree(st->dK[s]);
+        if (st->dq && st->dq[s]) cudaFree(st->dq[s]);
+        if (st->dout && st->dout[s]) cudaFree(st->dout[s]);
+    }
+    delete[] st->streams;
+    delete[] st->dK;
+    delete[] st->dq;
+    delete[] st->dout;
+    delete st;
+    return 0;
+}
+
+int noa_dcs_vmap_host_f64(noa_dcs_stager *st, int process, const double *h_K, const double *h_q,
+                          double *h_result, int64_t n, double A, double I, int32_t Z, double mass) {
+    if (!st || process < 0 || process > NOA_DCS_NPROCESS || n < 0) return NOA_DCS_EINVAL;
+    if (n == 0) return 0;
+    if (!h_K || !h_q || !h_result) return NOA_DCS_EINVAL;
+    const Params p = make_params(A, I, Z, mass);
+    int rc = 0;
+    int64_t c = 0;
+    for (int64_t off = 0; off < n && rc == 0; off += st->chunk, c++) {
+        const int s = (int) (c % st->n_slots);
+        const int64_t m = (n - off < st->chunk) ? (n - off) : st->chunk;
+        cudaStream_t stream = st->streams[s];
+        cudaError_t e = cudaMemcpyAsync(st->dK[s], h_K + off, m * sizeof(double),
+                                        cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(st->dq[s], h_q + off, m * sizeof(double), cudaMemcpyHostToDevice,
+                                stream);
+        if (e != cudaSuccess) {
+            rc = (int) e;
+            break;
+        }
+        if (process == NOA_DCS_NPROCESS) {
+            rc = vmap_all_impl(st->dK[s], st->dq[s], st->dout[s], m, p, stream);
+            for (int pr = 0; pr < NOA_DCS_NPROCESS && rc == 0; pr++)
+                rc = (int) cudaMemcpyAsync(h_result + (int64_t) pr * n + off,
+                                           st->dout[s] + (int64_t) pr * m, m * sizeof(double),
+                                           cudaMemcpyDeviceToHost, stream);
+        } else {
+            rc = vmap_impl(process, st->dK[s], st->dq[s], st->dout[s], m, p, stream);
+            if (rc == 0)
+                rc = (int) cudaMemcpyAsync(h_result + off, st->dout[s], m * sizeof(double),
+                                           cudaMemcpyDeviceToHost, stream);
+        }
+    }
+    for (int s = 0; s < st->n_slots; s++) {
+        cudaError_t e = cudaStreamSynchronize(st->streams[s]);
+        if (rc == 0 && e != cudaSuccess) rc = (int) e;
+    }
+    return rc;
+}
+
+int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink,
+                       void *stream) {
+    if (iters < 1 || blocks < 1 || threads < 1 || threads > 1024 || !sink) return NOA_DCS_EINVAL;
+    fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>>(iters, sink);
+    return after_launch();
+}
+
+int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t *sm_count) {
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    int b = 0;
+    switch (process) {
+        case 0: rc = persistent_grid(vmap_kernel<0, 2>, INT64_MAX / 2, b); break;
+        case 1: rc = persistent_grid(vmap_kernel<1, 1>, INT64_MAX / 2, b); break;
+        case 2: rc = persistent_grid(vmap_kernel<2, 1>, INT64_MAX / 2, b); break;
+        case 3: rc = persistent_grid(vmap_kernel<3, 2>, INT64_MAX / 2, b); break;
+        case 4: rc = persistent_grid(vmap_all_kernel, INT64_MAX / 2, b); break;
+        default: return NOA_DCS_EINVAL;
+    }
+    if (rc) return rc;
+    if (blocks) *blocks = b;
+    if (threads) *threads = kThreads;
+    if (sm_count) *sm_count = info.sm_count;
+    return 0;
+}
+
+}  // extern "C"

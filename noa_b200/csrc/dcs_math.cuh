@@ -53,6 +53,28 @@ struct Params {
                    0.0812743883615744, 0.0812743883615744, 0.3123470770400029,                \
                    0.3123470770400029, 0.2606106964029354, 0.2606106964029354}
 
+// Node/weight lookup: __constant__ memory on the device (uniform or near-uniform index), plain
+// static arrays in the host test build.
+#if defined(__CUDACC__)
+__constant__ double c_gl6_x[6] = NOA_GL6_X;
+__constant__ double c_gl6_w[6] = NOA_GL6_W;
+__constant__ double c_gl8_x[8] = NOA_GL8_X;
+__constant__ double c_gl8_w[8] = NOA_GL8_W;
+__constant__ double c_gl9_x[9] = NOA_GL9_X;
+__constant__ double c_gl9_w[9] = NOA_GL9_W;
+#endif
+static const double h_gl6_x[6] = NOA_GL6_X;
+static const double h_gl6_w[6] = NOA_GL6_W;
+static const double h_gl8_x[8] = NOA_GL8_X;
+static const double h_gl8_w[8] = NOA_GL8_W;
+static const double h_gl9_x[9] = NOA_GL9_X;
+static const double h_gl9_w[9] = NOA_GL9_W;
+#if defined(__CUDA_ARCH__)
+#define NOA_GL(rule, what, j) c_gl##rule##_##what[j]
+#else
+#define NOA_GL(rule, what, j) h_gl##rule##_##what[j]
+#endif
+
 // ------------------------------------------------------------------------------------------
 // Bremsstrahlung -- src/noa/pms/physics.hh:114-153
 // ------------------------------------------------------------------------------------------
@@ -170,11 +192,9 @@ NOA_HD double pair_finish(double K, double q, double integral, const PairKinemat
 NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tables &T) {
     PairKinematics k;
     if (!pair_setup(K, q, p, T, k)) return 0.;
-    const double xs[8] = NOA_GL8_X;
-    const double ws[8] = NOA_GL8_W;
     double acc = 0.;
 #pragma unroll 1
-    for (int j = 0; j < 8; j++) acc += pair_node(xs[j], q, k, p, T) * ws[j];
+    for (int j = 0; j < 8; j++) acc += pair_node(NOA_GL(8, x, j), q, k, p, T) * NOA_GL(8, w, j);
     return pair_finish(K, q, acc, k, p, T);
 }
 
@@ -279,11 +299,10 @@ NOA_HD double photonuclear_finish(double K, double ds, const PhotoKinematics &k,
 NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tables &T) {
     PhotoKinematics k;
     if (!photonuclear_setup(K, q, p, T, k)) return 0.;
-    const double xs[9] = NOA_GL9_X;
-    const double ws[9] = NOA_GL9_W;
     double acc = 0.;
 #pragma unroll 1
-    for (int j = 0; j < 9; j++) acc += photonuclear_node(xs[j], q, k, p, T) * ws[j];
+    for (int j = 0; j < 9; j++)
+        acc += photonuclear_node(NOA_GL(9, x, j), q, k, p, T) * NOA_GL(9, w, j);
     return photonuclear_finish(K, acc, k, p);
 }
 

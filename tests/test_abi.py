@@ -1,0 +1,64 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol the header declares,
+refuses to run without a device, and the Python mirror validates its arguments."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "noa_dcs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(noa_dcs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from noa_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/noa_dcs_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in noa_b200/_lib.py"
+    assert lib.noa_dcs_abi_version() == 1
+    assert b"invalid" in lib.noa_dcs_strerror(-1)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from noa_b200 import _lib, dcs, STANDARD_ROCK, MUON_MASS
+    with pytest.raises(_lib.NoaDcsError):
+        _lib.require_device()
+    K = torch.ones(4, dtype=torch.float64)
+    with pytest.raises((ValueError, _lib.NoaDcsError)):
+        dcs.map(dcs.bremsstrahlung)(K, K, STANDARD_ROCK, MUON_MASS)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "noa_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hh", ".cc", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "dcs_oracle" not in text and "libnoa_ref" not in text, f
+
+
+def test_api_tokens_and_validation():
+    import torch
+    from noa_b200 import dcs
+    assert [p.index for p in dcs.PROCESSES] == [0, 1, 2, 3]
+    with pytest.raises(TypeError):
+        dcs.vmap(lambda *a: 0.0)
+    with pytest.raises(TypeError):
+        dcs.vmap_integral(dcs.bremsstrahlung)
+    ri = dcs.recoil_integral(dcs.pair_production, dcs.cel_integrand)
+    assert ri.process.index == 1 and ri.integrand.index == 1
+    assert dcs.pvmap is dcs.vmap and dcs.pmap is dcs.map
+    bad = torch.ones(4, dtype=torch.float32)
+    with pytest.raises((ValueError, Exception)):
+        dcs.cuda.vmap_bremsstrahlung(bad, bad, bad, (22., 0.1364e-6, 11), 0.10565839)

@@ -1,0 +1,45 @@
+"""CPU pre-flight for the GPU parity tests: the kernels' scalar arithmetic, compiled for the host
+(oracle/hostcheck.cc), must agree BIT FOR BIT with (1) the system libm for exp/log/log10 and
+(2) the oracle for the four DCS and the closed-form ionisation integrals."""
+import ctypes
+
+import numpy as np
+
+from conftest import ELEMENTS, MUON_MASS
+from noa_b200 import grids
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def test_glibm_is_bit_exact_against_system_libm(hostcheck):
+    assert hostcheck.hostcheck_glibm(3_000_000, 20251017) == 0
+
+
+def test_kernel_math_on_host_matches_oracle_bit_for_bit(hostcheck, port):
+    for kind, (K, q) in (("A", grids.set_a(1 << 14)), ("B", grids.set_b(1 << 14))):
+        for en, el in ELEMENTS.items():
+            for p in range(4):
+                out = np.zeros_like(K)
+                rc = hostcheck.hostcheck_dcs(p, _p(K), _p(q), _p(out), ctypes.c_int64(K.size),
+                                             ctypes.c_double(el[0]), ctypes.c_double(el[1]),
+                                             ctypes.c_int32(el[2]), ctypes.c_double(MUON_MASS))
+                assert rc == 0
+                want = port.vmap(p, K, q, el, MUON_MASS, threads=4)
+                assert np.array_equal(out, want, equal_nan=True), (kind, en, p)
+
+
+def test_closed_form_ionisation_on_host(hostcheck, port):
+    K = grids.table_energies(256, -2.0, 1.0)     # below the 10.8 GeV switch (dcs.hh:964)
+    el = ELEMENTS["rock"]
+    for ig in (0, 1):
+        out = np.zeros_like(K)
+        hostcheck.hostcheck_ionisation_closed_form(ig, _p(K), _p(out), ctypes.c_int64(K.size),
+                                                   ctypes.c_double(0.05), ctypes.c_double(el[0]),
+                                                   ctypes.c_double(el[1]), ctypes.c_int32(el[2]),
+                                                   ctypes.c_double(MUON_MASS))
+        want = port.vmap_integral(3, ig, K, 0.05, 180, el, MUON_MASS)
+        assert np.array_equal(out, want)
