@@ -1,0 +1,76 @@
+"""CPU tests of the multi-GPU host logic: partitioning helpers and, with world_size = 2 under
+gloo, the cyclic table partition + all-gather + un-permute (the table arithmetic is stood in by
+the oracle so that no GPU is needed)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ELEMENTS, MUON_MASS, ROOT
+
+
+def test_shard_range_partitions_exactly():
+    from noa_b200.sharding import shard_range, cyclic_rows
+    for n in (0, 1, 7, 8, 9, 10000, (1 << 22) + 3):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+            if n < 100000:
+                rows = torch.cat([cyclic_rows(n, r, world) for r in range(world)])
+                assert sorted(rows.tolist()) == list(range(n))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_rows, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from noa_b200 import grids
+    from noa_b200.sharding import TableBuilder
+    checker = oracle.load_port()
+
+    def compute(K_local, xlow, element, mass, min_points, out, processes=None):
+        k = K_local.numpy()
+        for p in range(4):
+            out[0][p] = torch.from_numpy(checker.vmap_integral(p, 0, k, xlow, min_points, element, mass))
+            out[1][p] = torch.from_numpy(checker.vmap_integral(p, 1, k, xlow, min_points, element, mass))
+
+    K = torch.from_numpy(grids.table_energies(n_rows, -1.0, 4.0))
+    builder = TableBuilder(K, rank, world, compute=compute)
+    full = builder.build(0.05, ELEMENTS["rock"], MUON_MASS, 24)
+    np.save(os.path.join(tmp, f"table_{rank}.npy"), full.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows", [11, 16])
+def test_table_builder_world2_gloo(tmp_path, port, n_rows):
+    from noa_b200 import grids
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n_rows, str(tmp_path)), nprocs=world, join=True)
+    K = grids.table_energies(n_rows, -1.0, 4.0)
+    want = np.zeros((2, 4, n_rows))
+    for p in range(4):
+        for ig in range(2):
+            want[ig, p] = port.vmap_integral(p, ig, K, 0.05, 24, ELEMENTS["rock"], MUON_MASS)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"table_{r}.npy"))
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), f"rank {r}"
