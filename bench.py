@@ -145,20 +145,30 @@ def load_cpu_checker():
 
 
 def cpu_throughput(process, K, q, target_seconds, checker):
-    """evals/s of the reference CPU path (all host threads) on a bounded sample."""
+    """evals/s of the reference CPU path (all host threads).  The whole 2^22-pair workload takes
+    well under a second on a multi-core host, so the sample is the full workload repeated until
+    about `target_seconds` of CPU work has been done; the best pass is reported."""
     threads = checker.max_threads
-    probe = min(K.size, 1 << 15)
+    probe = min(K.size, 1 << 16)
     t = time.perf_counter()
     checker.vmap(process, K[:probe], q[:probe], ROCK, MUON_MASS, threads=threads)
     dt = max(time.perf_counter() - t, 1e-6)
     n = int(min(K.size, max(probe, probe * target_seconds / dt)))
-    # strided sample so the sample spans the same (K, q) distribution as the full workload
-    idx = np.linspace(0, K.size - 1, n).astype(np.int64)
-    Ks, qs = np.ascontiguousarray(K[idx]), np.ascontiguousarray(q[idx])
-    t = time.perf_counter()
-    checker.vmap(process, Ks, qs, ROCK, MUON_MASS, threads=threads)
-    dt = time.perf_counter() - t
-    return n / dt, n, threads, dt
+    if n < K.size:
+        # strided sample so it spans the same (K, q) distribution as the full workload
+        idx = np.linspace(0, K.size - 1, n).astype(np.int64)
+        Ks, qs = np.ascontiguousarray(K[idx]), np.ascontiguousarray(q[idx])
+    else:
+        Ks, qs = K, q
+    best, spent, passes = None, 0.0, 0
+    while passes < 1 or (spent < target_seconds and passes < 50):
+        t = time.perf_counter()
+        checker.vmap(process, Ks, qs, ROCK, MUON_MASS, threads=threads)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+        spent += dt
+        passes += 1
+    return n / best, n, threads, spent, passes
 
 
 def run_reference_arm(args):
@@ -382,10 +392,11 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1:
         checker, kind = load_cpu_checker()
-        rate, n_s, threads, dt = cpu_throughput(1, K0, q0, args.cpu_seconds, checker)
+        rate, n_s, threads, spent, passes = cpu_throughput(1, K0, q0, args.cpu_seconds, checker)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
-                        "sample": f"{n_s} of the 2^22 set-B pairs (evenly strided), "
-                                  f"dcs::pvmap(pair_production), {dt:.1f} s"}
+                        "sample": f"{n_s} of the 2^22 set-B pairs x {passes} passes "
+                                  f"({spent:.1f} s of dcs::pvmap(pair_production) on {threads} "
+                                  f"OpenMP threads), best pass"}
 
     if rank == 0:
         line = {

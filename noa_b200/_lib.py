@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnoa_dcs_b200.so")
+# NOA_DCS_LIB: developer hook to load an alternative build of the same library (kernel experiments)
+LIB_PATH = os.environ.get("NOA_DCS_LIB") or os.path.join(_HERE, "libnoa_dcs_b200.so")
 
 _c_double_p = ctypes.c_void_p   # raw addresses (device or host)
 _i64 = ctypes.c_int64

@@ -34,6 +34,33 @@ __device__ const glibm::Tables g_tables = {GLIBM_EXP_TABLE_INIT, GLIBM_LOG_TABLE
 
 constexpr int kThreads = 256;
 
+// Minimum resident CTAs per SM requested from ptxas (register cap = 65536 / (256 * N)).
+// The kernels are bound by issue slots and fixed-latency dependencies, not by the FP64 pipe alone
+// (profiles/), so occupancy matters; values chosen by measurement (gpurun sweep of
+// tools/variant_sweep.sh): pair/photonuclear 4 (64 registers), fused kernels 3,
+// table kernel 4 (a few spilled bytes are cheaper than a lost CTA).  The two streaming kernels
+// need < 50 registers anyway.
+#ifndef NOA_MINB_PAIR
+#define NOA_MINB_PAIR 4
+#endif
+#ifndef NOA_MINB_PHOTO
+#define NOA_MINB_PHOTO 4
+#endif
+#ifndef NOA_MINB_STREAM
+#define NOA_MINB_STREAM 5
+#endif
+#ifndef NOA_MINB_ALL
+#define NOA_MINB_ALL 3
+#endif
+#ifndef NOA_MINB_TABLE
+#define NOA_MINB_TABLE 4
+#endif
+template <int PROCESS>
+struct MinBlocks {
+    static constexpr int value = (PROCESS == 1) ? NOA_MINB_PAIR
+                                 : (PROCESS == 2) ? NOA_MINB_PHOTO : NOA_MINB_STREAM;
+};
+
 // 4 KB global -> shared, coalesced 128-bit copies
 __device__ __forceinline__ void stage_tables(glibm::Tables &dst) {
     const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
@@ -47,7 +74,7 @@ __device__ __forceinline__ void stage_tables(glibm::Tables &dst) {
 // element-wise, one process
 // ------------------------------------------------------------------------------------------
 template <int PROCESS, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MinBlocks<PROCESS>::value)
 vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *__restrict__ out,
             int64_t n, const __grid_constant__ Params p) {
     __shared__ glibm::Tables T;
@@ -102,7 +129,7 @@ vmap_pair_lanes_kernel(const double *__restrict__ K, const double *__restrict__ 
 }
 
 // element-wise, all four processes of a pair: out[p * n + i]
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
 vmap_all_kernel(const double *__restrict__ K, const double *__restrict__ q,
                 double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
     __shared__ glibm::Tables T;
@@ -134,7 +161,7 @@ __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, 
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
 vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
                     double *__restrict__ out, int64_t n, const __grid_constant__ Mixture m) {
     __shared__ glibm::Tables T;
@@ -170,7 +197,7 @@ struct TablePlan {
     double xlow;
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
 table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
              double *__restrict__ cel, const __grid_constant__ TablePlan plan,
              const __grid_constant__ Params p) {
