@@ -1,0 +1,74 @@
+// pybind11 torch extension with the surface of the reference's notebook extensions
+// docs/pms/muon_dcs.cu:8-16 (`bremsstrahlung` on CUDA) and docs/pms/muon_dcs.cc:8-45 (the four
+// processes + `serialise`), all on the GPU: standard rock, muon, GIL released during the call.
+// It goes through the LibTorch boundary (torch_api.cc), i.e. exactly what a C++ user links.
+#include "../../include/noa_b200/pms_dcs_cuda.hh"
+
+#include <torch/extension.h>
+
+using namespace noa::pms;
+
+inline torch::Tensor bremsstrahlung(torch::Tensor kinetic_energies, torch::Tensor recoil_energies) {
+    return dcs::cuda::map_bremsstrahlung(kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                         MUON_MASS);
+}
+
+inline torch::Tensor pair_production(torch::Tensor kinetic_energies,
+                                     torch::Tensor recoil_energies) {
+    return dcs::cuda::map_pair_production(kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                          MUON_MASS);
+}
+
+inline torch::Tensor photonuclear(torch::Tensor kinetic_energies, torch::Tensor recoil_energies) {
+    return dcs::cuda::map_photonuclear(kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                       MUON_MASS);
+}
+
+inline torch::Tensor ionisation(torch::Tensor kinetic_energies, torch::Tensor recoil_energies) {
+    return dcs::cuda::map_ionisation(kinetic_energies, recoil_energies, STANDARD_ROCK, MUON_MASS);
+}
+
+inline torch::Tensor all_processes(torch::Tensor kinetic_energies, torch::Tensor recoil_energies) {
+    return dcs::cuda::map_all(kinetic_energies, recoil_energies, STANDARD_ROCK, MUON_MASS);
+}
+
+inline torch::Tensor tables(torch::Tensor kinetic_energies, double xlow, int min_points) {
+    return dcs::cuda::tables(kinetic_energies, xlow, STANDARD_ROCK, MUON_MASS, min_points);
+}
+
+inline torch::Tensor recoil_integral(int process, int integrand, torch::Tensor kinetic_energies,
+                                     double xlow, int min_points) {
+    const auto result = torch::empty_like(kinetic_energies);
+    dcs::cuda::vmap_integral(process, integrand, result, kinetic_energies, xlow, STANDARD_ROCK,
+                             MUON_MASS, min_points);
+    return result;
+}
+
+inline torch::Tensor water(torch::Tensor kinetic_energies, torch::Tensor recoil_energies) {
+    return dcs::cuda::map_material(kinetic_energies, recoil_energies,
+                                   {AtomicElement{1.0087, 19.2E-9, 1},
+                                    AtomicElement{15.999, 95.0E-9, 8}},
+                                   {0.111894, 0.888106}, MUON_MASS);
+}
+
+inline void serialise(torch::Tensor tensor, std::string path) { torch::save(tensor, path); }
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("bremsstrahlung", &bremsstrahlung, py::call_guard<py::gil_scoped_release>(),
+          "Standard Rock Bremsstrahlung DCS for Muons on CUDA");
+    m.def("pair_production", &pair_production, py::call_guard<py::gil_scoped_release>(),
+          "Standard Rock Pair production DCS for Muons on CUDA");
+    m.def("photonuclear", &photonuclear, py::call_guard<py::gil_scoped_release>(),
+          "Standard Rock Photonuclear DCS for Muons on CUDA");
+    m.def("ionisation", &ionisation, py::call_guard<py::gil_scoped_release>(),
+          "Standard Rock Ionisation DCS for Muons on CUDA");
+    m.def("all_processes", &all_processes, py::call_guard<py::gil_scoped_release>(),
+          "The four DCS in one pass, [4, n]");
+    m.def("tables", &tables, py::call_guard<py::gil_scoped_release>(),
+          "DEL/CEL tables [2, 4, n_K] for standard rock");
+    m.def("recoil_integral", &recoil_integral, py::call_guard<py::gil_scoped_release>(),
+          "vmap_integral(recoil_integral(process, integrand)) for standard rock");
+    m.def("water", &water, py::call_guard<py::gil_scoped_release>(),
+          "The four DCS on water (H + O mass-fraction mix), [4, n]");
+    m.def("serialise", &serialise, py::call_guard<py::gil_scoped_release>(), "Save tensor to disk");
+}

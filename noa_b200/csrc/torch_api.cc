@@ -1,0 +1,174 @@
+// LibTorch boundary: defines noa::pms::dcs::cuda::* (include/noa_b200/pms_dcs_cuda.hh) on top of
+// the C ABI (include/noa_dcs_b200.h).  Compiled by the host compiler only -- no nvcc, no kernels
+// here -- so it builds in about a minute despite <torch/...> (the reference's dcs.cuh TU needs
+// ~5 min under nvcc).
+#include "../../include/noa_b200/pms_dcs_cuda.hh"
+#include "../../include/noa_dcs_b200.h"
+
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/torch.h>
+
+namespace noa::pms::dcs::cuda {
+
+    namespace {
+        void check_tensor(const torch::Tensor &t, const char *name) {
+            TORCH_CHECK(t.defined(), name, " is undefined");
+            TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor (this build has no CPU path)");
+            TORCH_CHECK(t.scalar_type() == torch::kFloat64, name, " must be float64, got ",
+                        t.scalar_type());
+            TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+        }
+
+        void check_pair(const torch::Tensor &K, const torch::Tensor &q) {
+            check_tensor(K, "kinetic_energies");
+            check_tensor(q, "recoil_energies");
+            TORCH_CHECK(K.numel() == q.numel(), "kinetic_energies and recoil_energies differ in "
+                        "size: ", K.numel(), " vs ", q.numel());
+            TORCH_CHECK(K.device() == q.device(), "tensors are on different devices");
+        }
+
+        void check_rc(int rc, const char *what) {
+            TORCH_CHECK(rc == 0, what, " failed: ", noa_dcs_strerror(rc), " (", rc, ")");
+        }
+
+        void *current_stream(const torch::Tensor &t) {
+            return (void *) c10::cuda::getCurrentCUDAStream(t.device().index()).stream();
+        }
+
+        void vmap_process(int process, const Calculation &result, const Energies &K,
+                          const Energies &q, const AtomicElement &el, const ParticleMass &mass) {
+            check_pair(K, q);
+            check_tensor(result, "result");
+            TORCH_CHECK(result.numel() == K.numel(), "result has ", result.numel(),
+                        " elements, expected ", K.numel());
+            TORCH_CHECK(result.device() == K.device(), "result is on a different device");
+            const c10::cuda::CUDAGuard guard(K.device());
+            check_rc(noa_dcs_vmap_f64(process, K.data_ptr<double>(), q.data_ptr<double>(),
+                                      result.data_ptr<double>(), K.numel(), el.A, el.I, el.Z, mass,
+                                      current_stream(K)),
+                     "noa_dcs_vmap_f64");
+        }
+
+        Calculation map_process(int process, const Energies &K, const Energies &q,
+                                const AtomicElement &el, const ParticleMass &mass) {
+            // the reference allocates zeros_like (dcs.cuh:48); every element is overwritten
+            const auto result = torch::empty_like(K);
+            vmap_process(process, result, K, q, el, mass);
+            return result;
+        }
+    }  // namespace
+
+#define NOA_B200_DEFINE_PROCESS(NAME, ID)                                                        \
+    void vmap_##NAME(const Calculation &result, const Energies &kinetic_energies,                \
+                     const Energies &recoil_energies, const AtomicElement &element,              \
+                     const ParticleMass &mass) {                                                 \
+        vmap_process(ID, result, kinetic_energies, recoil_energies, element, mass);              \
+    }                                                                                            \
+    Calculation map_##NAME(const Energies &kinetic_energies, const Energies &recoil_energies,    \
+                           const AtomicElement &element, const ParticleMass &mass) {             \
+        return map_process(ID, kinetic_energies, recoil_energies, element, mass);                \
+    }
+
+    NOA_B200_DEFINE_PROCESS(bremsstrahlung, NOA_DCS_BREMSSTRAHLUNG)
+    NOA_B200_DEFINE_PROCESS(pair_production, NOA_DCS_PAIR_PRODUCTION)
+    NOA_B200_DEFINE_PROCESS(photonuclear, NOA_DCS_PHOTONUCLEAR)
+    NOA_B200_DEFINE_PROCESS(ionisation, NOA_DCS_IONISATION)
+#undef NOA_B200_DEFINE_PROCESS
+
+    void vmap_all(const Calculation &result, const Energies &K, const Energies &q,
+                  const AtomicElement &el, const ParticleMass &mass) {
+        check_pair(K, q);
+        check_tensor(result, "result");
+        TORCH_CHECK(result.numel() == 4 * K.numel(), "result must hold 4 x ", K.numel(),
+                    " elements");
+        const c10::cuda::CUDAGuard guard(K.device());
+        check_rc(noa_dcs_vmap_all_f64(K.data_ptr<double>(), q.data_ptr<double>(),
+                                      result.data_ptr<double>(), K.numel(), el.A, el.I, el.Z, mass,
+                                      current_stream(K)),
+                 "noa_dcs_vmap_all_f64");
+    }
+
+    Calculation map_all(const Energies &K, const Energies &q, const AtomicElement &el,
+                        const ParticleMass &mass) {
+        auto shape = K.sizes().vec();
+        shape.insert(shape.begin(), 4);
+        const auto result = torch::empty(shape, K.options());
+        vmap_all(result, K, q, el, mass);
+        return result;
+    }
+
+    Calculation map_material(const Energies &K, const Energies &q,
+                             const std::vector<AtomicElement> &elements,
+                             const std::vector<Scalar> &mass_fractions, const ParticleMass &mass) {
+        check_pair(K, q);
+        TORCH_CHECK(!elements.empty() && elements.size() == mass_fractions.size() &&
+                    elements.size() <= NOA_DCS_MAX_ELEMENTS,
+                    "a material has 1..", NOA_DCS_MAX_ELEMENTS, " elements with one mass fraction "
+                    "each");
+        std::vector<double> A, I;
+        std::vector<int32_t> Z;
+        for (const auto &e : elements) {
+            A.push_back(e.A);
+            I.push_back(e.I);
+            Z.push_back(e.Z);
+        }
+        auto shape = K.sizes().vec();
+        shape.insert(shape.begin(), 4);
+        const auto result = torch::empty(shape, K.options());
+        const c10::cuda::CUDAGuard guard(K.device());
+        check_rc(noa_dcs_vmap_mixture_f64(0xFu, K.data_ptr<double>(), q.data_ptr<double>(),
+                                          result.data_ptr<double>(), K.numel(),
+                                          (int32_t) elements.size(), A.data(), I.data(), Z.data(),
+                                          mass_fractions.data(), mass, current_stream(K)),
+                 "noa_dcs_vmap_mixture_f64");
+        return result;
+    }
+
+    void vmap_integral(int process, int integrand, const Calculation &result, const Energies &K,
+                       const EnergyTransfer &xlow, const AtomicElement &el,
+                       const ParticleMass &mass, const Index min_points) {
+        check_tensor(K, "kinetic_energies");
+        check_tensor(result, "result");
+        TORCH_CHECK(result.numel() == K.numel(), "result has ", result.numel(),
+                    " elements, expected ", K.numel());
+        const c10::cuda::CUDAGuard guard(K.device());
+        check_rc(noa_dcs_vmap_integral_f64(process, integrand, K.data_ptr<double>(),
+                                           result.data_ptr<double>(), K.numel(), xlow, min_points,
+                                           el.A, el.I, el.Z, mass, current_stream(K)),
+                 "noa_dcs_vmap_integral_f64");
+    }
+
+#define NOA_B200_DEFINE_INTEGRAL(NAME, ID)                                                        \
+    void vmap_del_integral_##NAME(const Calculation &result, const Energies &K,                   \
+                                  const EnergyTransfer &xlow, const AtomicElement &element,       \
+                                  const ParticleMass &mass, const Index min_points) {             \
+        vmap_integral(ID, 0, result, K, xlow, element, mass, min_points);                         \
+    }                                                                                             \
+    void vmap_cel_integral_##NAME(const Calculation &result, const Energies &K,                   \
+                                  const EnergyTransfer &xlow, const AtomicElement &element,       \
+                                  const ParticleMass &mass, const Index min_points) {             \
+        vmap_integral(ID, 1, result, K, xlow, element, mass, min_points);                         \
+    }
+
+    NOA_B200_DEFINE_INTEGRAL(bremsstrahlung, NOA_DCS_BREMSSTRAHLUNG)
+    NOA_B200_DEFINE_INTEGRAL(pair_production, NOA_DCS_PAIR_PRODUCTION)
+    NOA_B200_DEFINE_INTEGRAL(photonuclear, NOA_DCS_PHOTONUCLEAR)
+    NOA_B200_DEFINE_INTEGRAL(ionisation, NOA_DCS_IONISATION)
+#undef NOA_B200_DEFINE_INTEGRAL
+
+    Calculation tables(const Energies &K, const EnergyTransfer &xlow, const AtomicElement &el,
+                       const ParticleMass &mass, const Index min_points) {
+        check_tensor(K, "kinetic_energies");
+        const auto result = torch::zeros({2, 4, K.numel()}, K.options());
+        if (K.numel() == 0) return result;
+        const c10::cuda::CUDAGuard guard(K.device());
+        double *base = result.data_ptr<double>();
+        check_rc(noa_dcs_table_f64(0xFu, K.data_ptr<double>(), K.numel(), xlow, min_points, el.A,
+                                   el.I, el.Z, mass, base, base + 4 * K.numel(),
+                                   current_stream(K)),
+                 "noa_dcs_table_f64");
+        return result;
+    }
+
+}  // namespace noa::pms::dcs::cuda

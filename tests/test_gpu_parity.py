@@ -238,3 +238,27 @@ def test_runs_on_a_side_stream(port):
         out = dcs.map(dcs.photonuclear)(Kd, qd, ELEMENTS["rock"], MUON_MASS)
     s.synchronize()
     assert_parity(out, port.vmap(2, K, q, ELEMENTS["rock"], MUON_MASS, threads=8), "side stream")
+
+
+def test_cpp_libtorch_boundary_via_pybind(golden):
+    """The C++ API (noa::pms::dcs::cuda::*, csrc/torch_api.cc) through the muon_dcs pybind module
+    that mirrors docs/pms/muon_dcs.{cc,cu}."""
+    from noa_b200 import muons
+    K, q = dev(golden["N_K"]), dev(golden["N_q"])
+    for name in PROC:
+        got = getattr(muons, name)(K, q)
+        assert_parity(got, golden[f"vmap_N_rock_{name}"], ("muons", name))
+    allp = muons.all_processes(K, q)
+    assert allp.shape == (4, K.numel())
+    assert_parity(allp[1], golden["vmap_N_rock_pair_production"], "muons.all_processes")
+    Kt = dev(golden["T_K"])
+    t = muons.tables(Kt, 0.05, 180)
+    assert t.shape == (2, 4, Kt.numel())
+    assert_parity(t[0, 2], golden["integral_rock_photonuclear_del_180"], "muons.tables del")
+    assert_parity(t[1, 3], golden["integral_rock_ionisation_cel_180"], "muons.tables cel")
+    col = muons.recoil_integral(0, 1, Kt, 0.05, 1000)
+    assert_parity(col, golden["integral_rock_bremsstrahlung_cel_1000"], "muons.recoil_integral")
+    with pytest.raises(RuntimeError):
+        muons.bremsstrahlung(K.float(), q.float())
+    with pytest.raises(RuntimeError):
+        muons.bremsstrahlung(K.cpu(), q.cpu())
