@@ -139,9 +139,9 @@ class ClockSampler:
 def load_cpu_checker():
     import oracle
     ref = oracle.load_reference()
-    if ref is not None:
-        return ref, "reference"
-    return oracle.load_port(), "port"
+    checker, kind = (ref, "reference") if ref is not None else (oracle.load_port(), "port")
+    checker.use_all_cores()
+    return checker, kind
 
 
 def cpu_throughput(process, K, q, target_seconds, checker):

@@ -46,6 +46,18 @@ class Checker:
         thr.restype = ctypes.c_int
         self.max_threads = int(thr())
 
+    def use_all_cores(self):
+        """Size the OpenMP team to the cores this process may run on (torchrun exports
+        OMP_NUM_THREADS=1, which would make the 'all host threads' baseline single-threaded)."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        if self.kind == "reference" and hasattr(self._lib, "noa_ref_set_threads"):
+            self._lib.noa_ref_set_threads(ctypes.c_int(n))
+        self.max_threads = n
+        return n
+
     def _threads_arg(self, threads):
         # the port takes a thread count, the reference shim a serial/OpenMP switch
         # (OpenMP team size of the reference = OMP_NUM_THREADS / all cores)

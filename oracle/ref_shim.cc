@@ -53,6 +53,9 @@ extern "C" {
 
 int noa_ref_threads() { return omp_get_max_threads(); }
 
+// torchrun exports OMP_NUM_THREADS=1; the bench's reference arm restores the host's core count
+void noa_ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 // process: 0 brems, 1 pair, 2 photonuclear, 3 ionisation
 int noa_ref_vmap(int process, int parallel, const double *K, const double *q, double *out,
                  int64_t n, double A, double I, int32_t Z, double mass) {
