@@ -61,13 +61,15 @@ struct MinBlocks {
                                  : (PROCESS == 2) ? NOA_MINB_PHOTO : NOA_MINB_STREAM;
 };
 
-// 4 KB global -> shared, coalesced 128-bit copies
-__device__ __forceinline__ void stage_tables(glibm::Tables &dst) {
+// 4 KB global -> shared, coalesced 128-bit copies; returns the shared-window addresses the
+// lookups use
+__device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
     const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
     uint4 *d = reinterpret_cast<uint4 *>(&dst);
     for (int i = threadIdx.x; i < (int) (sizeof(glibm::Tables) / sizeof(uint4)); i += blockDim.x)
         d[i] = src[i];
     __syncthreads();
+    return glibm::make_smem_tab(dst);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -77,8 +79,8 @@ template <int PROCESS, int VEC>
 __global__ void __launch_bounds__(kThreads, MinBlocks<PROCESS>::value)
 vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *__restrict__ out,
             int64_t n, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables T;
-    stage_tables(T);
+    __shared__ glibm::Tables s_tables;
+    const glibm::Tab T = stage_tables(s_tables);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (VEC == 2) {
@@ -104,8 +106,8 @@ vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *
 __global__ void __launch_bounds__(kThreads)
 vmap_pair_lanes_kernel(const double *__restrict__ K, const double *__restrict__ q,
                        double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables T;
-    stage_tables(T);
+    __shared__ glibm::Tables s_tables;
+    const glibm::Tab T = stage_tables(s_tables);
     const int lane = threadIdx.x & 31;
     const int node = lane & 7;
     const int64_t groups = ((int64_t) gridDim.x * blockDim.x) >> 3;
@@ -132,8 +134,8 @@ vmap_pair_lanes_kernel(const double *__restrict__ K, const double *__restrict__ 
 __global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
 vmap_all_kernel(const double *__restrict__ K, const double *__restrict__ q,
                 double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables T;
-    stage_tables(T);
+    __shared__ glibm::Tables s_tables;
+    const glibm::Tab T = stage_tables(s_tables);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double k = K[i], r = q[i];
@@ -152,7 +154,7 @@ struct Mixture {
 };
 
 __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, const Params &p,
-                                               const glibm::Tables &T) {
+                                               const glibm::Tab &T) {
     switch (process) {
         case 0: return bremsstrahlung(k, r, p, T);
         case 1: return pair_production(k, r, p, T);
@@ -164,8 +166,8 @@ __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, 
 __global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
 vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
                     double *__restrict__ out, int64_t n, const __grid_constant__ Mixture m) {
-    __shared__ glibm::Tables T;
-    stage_tables(T);
+    __shared__ glibm::Tables s_tables;
+    const glibm::Tab T = stage_tables(s_tables);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double k = K[i], r = q[i];
@@ -201,10 +203,10 @@ __global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
 table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
              double *__restrict__ cel, const __grid_constant__ TablePlan plan,
              const __grid_constant__ Params p) {
-    __shared__ glibm::Tables T;
+    __shared__ glibm::Tables s_tables;
     __shared__ double s_del[kTableChunk];
     __shared__ double s_cel[kTableChunk];
-    stage_tables(T);
+    const glibm::Tab T = stage_tables(s_tables);
 
     const int64_t b = blockIdx.x;
     const int process = plan.process[b / nK];
@@ -219,8 +221,8 @@ table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
         return;
     }
 
-    const double lb = glibm::log(k * plan.xlow, T.log_tab);
-    const double ub = glibm::log(k, T.log_tab);
+    const double lb = glibm::log(k * plan.xlow, T);
+    const double ub = glibm::log(k, T);
     const double h = (ub - lb) / plan.cells;
     const uint32_t total = plan.cells * 6u;
     double acc = 0.;
@@ -229,7 +231,7 @@ table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
         for (uint32_t i = base + tid; i < base + count; i += kThreads) {
             const uint32_t j = i % 6u;
             const double x = lb + h * ((i / 6u) + c_gl6_x[j]);
-            const double r = glibm::exp(x, T.exp_tab);
+            const double r = glibm::exp(x, T);
             const double f = dcs_dispatch(process, k, r, p, T);
             const double w = c_gl6_w[j];
             const double fr = f * r;

@@ -78,7 +78,7 @@ static const double h_gl9_w[9] = NOA_GL9_W;
 // ------------------------------------------------------------------------------------------
 // Bremsstrahlung -- src/noa/pms/physics.hh:114-153
 // ------------------------------------------------------------------------------------------
-NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tables &T) {
+NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tab &T) {
     const double me = kElectronMass;
     const double sqrte = 1.648721271;
     const double E = K + p.mass;
@@ -87,13 +87,11 @@ NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::T
     const double nu = q / E;
     const double delta = delta_factor * nu / (1. - nu);
     double phi_n = glibm::log(p.b_bzn * (p.mass + delta * p.b_c1) /
-                                  (p.b_dn * (me + delta * sqrte * p.b_bzn)),
-                              T.log_tab);
+                                  (p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
     if (phi_n < 0.) phi_n = 0.;
     double phi_e = 0.;
     if (q < qe_max) {
-        phi_e = glibm::log(p.b_bzem / ((1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)),
-                           T.log_tab);
+        phi_e = glibm::log(p.b_bzem / ((1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
         if (phi_e < 0.) phi_e = 0.;
     }
     const double s = p.b_pref * (p.Zd * phi_n + phi_e) * (4. / 3. * (1. / nu - 1.) + nu);
@@ -108,7 +106,7 @@ struct PairKinematics {   // per-(K,q) quantities of src/noa/pms/dcs.hh:159-176
 };
 
 // Kinematic window and integration bound; false = the DCS is exactly 0 (dcs.hh:151-156,174-175)
-NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tables &T,
+NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tab &T,
                        PairKinematics &k) {
     if (q <= 4. * kElectronMass) return false;
     if (q >= K + p.p_thr) return false;
@@ -120,15 +118,15 @@ NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tables 
     const double x1 = 6. / (k.gamma * (k.gamma - q / p.mass));
     const double argmin = (x0 + 2. * (1. - x0) * x1) / (1. + (1. - x1) * sqrt(1. - x0));
     if ((argmin >= 1.) || (argmin <= 0.)) return false;
-    k.tmin = glibm::log(argmin, T.log_tab);
+    k.tmin = glibm::log(argmin, T);
     return true;
 }
 
 // Integrand of the t = ln(1-rho) integral at node t (dcs.hh:179-227)
 NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Params &p,
-                        const glibm::Tables &T) {
+                        const glibm::Tab &T) {
     const double beta = k.beta;
-    const double eps = glibm::exp(t * k.tmin, T.exp_tab);
+    const double eps = glibm::exp(t * k.tmin, T);
     const double rho = 1. - eps;
     const double rho2 = rho * rho;
     const double rho21 = eps * (2. - eps);
@@ -139,15 +137,15 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
     if (xi >= 1E+03)
         Be = 0.5 * xi_i * ((3 - rho2) + 2. * beta * (1. + rho2));
     else
-        Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) * glibm::log(1. + xi_i, T.log_tab) +
+        Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) * glibm::log(1. + xi_i, T) +
              (rho21 - beta) / (1. + xi) - 3. - rho2;
     const double Ye = (5. - rho2 + 4. * beta * (1. + rho2)) /
-                      (2. * (1. + 3. * beta) * glibm::log(3. + xi_i, T.log_tab) - rho2 -
+                      (2. * (1. + 3. * beta) * glibm::log(3. + xi_i, T) - rho2 -
                        2. * beta * (2. - rho2));
     const double xe = (1. + xi) * (1. + Ye);
     const double cLi = p.p_cl / rho21;
-    const double Le = glibm::log(p.p_az13 * sqrt(xe) * q / (q + cLi * xe), T.log_tab) -
-                      0.5 * glibm::log(1. + p.p_cle * xe, T.log_tab);
+    const double Le = glibm::log(p.p_az13 * sqrt(xe) * q / (q + cLi * xe), T) -
+                      0.5 * glibm::log(1. + p.p_cle * xe, T);
     double phi_e = Be * Le;
     if (phi_e < 0.) phi_e = 0.;
 
@@ -156,13 +154,13 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
         Bmu = 0.5 * xi * (5. - rho2 + beta * (3. + rho2));
     else
         Bmu = ((1. + rho2) * (1. + 1.5 * beta) - xi_i * (1. + 2. * beta) * rho21) *
-                  glibm::log(1. + xi, T.log_tab) +
+                  glibm::log(1. + xi, T) +
               xi * (rho21 - beta) / (1. + xi) + (1. + 2. * beta) * rho21;
     const double Ymu = (4. + rho2 + 3. * beta * (1. + rho2)) /
-                       ((1. + rho2) * (1.5 + 2. * beta) * glibm::log(3. + xi, T.log_tab) + 1. -
+                       ((1. + rho2) * (1.5 + 2. * beta) * glibm::log(3. + xi, T) + 1. -
                         1.5 * rho2);
     const double xmu = (1. + xi) * (1. + Ymu);
-    const double Lmu = glibm::log(p.p_raz13 * q / (p.p_z15 * (q + cLi * xmu)), T.log_tab);
+    const double Lmu = glibm::log(p.p_raz13 * q / (p.p_z15 * (q + cLi * xmu)), T);
     double phi_mu = Bmu * Lmu;
     if (phi_mu < 0.) phi_mu = 0.;
     return -(phi_e + phi_mu / p.p_r2) * (1. - rho) * k.tmin;
@@ -170,18 +168,18 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
 
 // Atomic-electron form factor and normalisation (dcs.hh:229-257); `integral` is the 8-node sum
 NOA_HD double pair_finish(double K, double q, double integral, const PairKinematics &k,
-                          const Params &p, const glibm::Tables &T) {
+                          const Params &p, const glibm::Tab &T) {
     const double gamma = k.gamma;
     double zeta;
     if (gamma <= 35.)
         zeta = 0.;
     else {
-        zeta = 0.073 * glibm::log(gamma / (1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T.log_tab) -
+        zeta = 0.073 * glibm::log(gamma / (1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
                0.26;
         if (zeta <= 0.)
             zeta = 0.;
         else
-            zeta /= 0.058 * glibm::log(gamma / (1. + p.p_g2 * gamma * p.p_z13), T.log_tab) - 0.14;
+            zeta /= 0.058 * glibm::log(gamma / (1. + p.p_g2 * gamma * p.p_z13), T) - 0.14;
     }
     const double E = K + p.mass;
     const double s = p.p_cz * (p.Zd + zeta) * (E - q) * integral / (q * E);
@@ -189,7 +187,7 @@ NOA_HD double pair_finish(double K, double q, double integral, const PairKinemat
 }
 
 // One thread does all 8 nodes; accumulation order of numerics.hh:84-87 (h = 1, lb = 0)
-NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tables &T) {
+NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T) {
     PairKinematics k;
     if (!pair_setup(K, q, p, T, k)) return 0.;
     double acc = 0.;
@@ -202,7 +200,7 @@ NOA_HD double pair_production(double K, double q, const Params &p, const glibm::
 // Photonuclear -- src/noa/pms/dcs.hh:261-405
 // ------------------------------------------------------------------------------------------
 // ALLM97 F2 (dcs.hh:261-307)
-NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tables &T) {
+NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T) {
     const double m02 = 0.31985, mP2 = 49.457, mR2 = 0.15052, Q02 = 0.52544, Lambda2 = 0.06527;
     const double cP1 = 0.28067, cP2 = 0.22291, cP3 = 2.1979;
     const double aP1 = -0.0808, aP2 = -0.44812, aP3 = 1.1709;
@@ -213,40 +211,39 @@ NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tables 
     const double M2 = 0.8803505929;
 
     const double W2 = M2 + Q2 * (1.0 / x - 1.0);
-    const double t = glibm::log(glibm::log((Q2 + Q02) / Lambda2, T.log_tab) / p.n_logq0l,
-                                T.log_tab);
+    const double t = glibm::log(glibm::log((Q2 + Q02) / Lambda2, T) / p.n_logq0l, T);
     const double xP = (Q2 + mP2) / (Q2 + mP2 + W2 - M2);
     const double xR = (Q2 + mR2) / (Q2 + mR2 + W2 - M2);
-    const double lnt = glibm::log(t, T.log_tab);
-    const double cP = cP1 + (cP1 - cP2) * (1.0 / (1.0 + glibm::exp(cP3 * lnt, T.exp_tab)) - 1.0);
-    const double aP = aP1 + (aP1 - aP2) * (1.0 / (1.0 + glibm::exp(aP3 * lnt, T.exp_tab)) - 1.0);
-    const double bP = bP1 + bP2 * glibm::exp(bP3 * lnt, T.exp_tab);
-    const double cR = cR1 + cR2 * glibm::exp(cR3 * lnt, T.exp_tab);
-    const double aR = aR1 + aR2 * glibm::exp(aR3 * lnt, T.exp_tab);
-    const double bR = bR1 + bR2 * glibm::exp(bR3 * lnt, T.exp_tab);
+    const double lnt = glibm::log(t, T);
+    const double cP = cP1 + (cP1 - cP2) * (1.0 / (1.0 + glibm::exp(cP3 * lnt, T)) - 1.0);
+    const double aP = aP1 + (aP1 - aP2) * (1.0 / (1.0 + glibm::exp(aP3 * lnt, T)) - 1.0);
+    const double bP = bP1 + bP2 * glibm::exp(bP3 * lnt, T);
+    const double cR = cR1 + cR2 * glibm::exp(cR3 * lnt, T);
+    const double aR = aR1 + aR2 * glibm::exp(aR3 * lnt, T);
+    const double bR = bR1 + bR2 * glibm::exp(bR3 * lnt, T);
 
-    const double l1x = glibm::log(1 - x, T.log_tab);
-    const double F2P = cP * glibm::exp(aP * glibm::log(xP, T.log_tab) + bP * l1x, T.exp_tab);
-    const double F2R = cR * glibm::exp(aR * glibm::log(xR, T.log_tab) + bR * l1x, T.exp_tab);
+    const double l1x = glibm::log(1 - x, T);
+    const double F2P = cP * glibm::exp(aP * glibm::log(xP, T) + bP * l1x, T);
+    const double F2R = cR * glibm::exp(aR * glibm::log(xR, T) + bR * l1x, T);
     return Q2 / (Q2 + m02) * (F2P + F2R);
 }
 
 // DRSS shadowing (dcs.hh:310-319)
-NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tables &T) {
+NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tab &T) {
     double a = 1.0;
     if (x < 0.0014)
         a = p.n_alow;
     else if (x < 0.04)
-        a = glibm::exp((0.069 * glibm::log10(x, T.log_tab) + 0.097) * p.n_logA, T.exp_tab);
+        a = glibm::exp((0.069 * glibm::log10(x, T) + 0.097) * p.n_logA, T);
     return (p.n_halfA * a * (2.0 + x * (-1.85 + x * (2.45 + x * (-2.35 + x)))) * F2p);
 }
 
 // Whitlow R (dcs.hh:322-332)
-NOA_HD double r_whitlow(double x, double Q2, const glibm::Tables &T) {
+NOA_HD double r_whitlow(double x, double Q2, const glibm::Tab &T) {
     double q2 = Q2;
     if (Q2 < 0.3) q2 = 0.3;
     const double theta = 1 + 12.0 * q2 / (1.0 + q2) * 0.015625 / (0.015625 + x * x);
-    return (0.635 / glibm::log(q2 / 0.04, T.log_tab) * theta + 0.5747 / q2 -
+    return (0.635 / glibm::log(q2 / 0.04, T) * theta + 0.5747 / q2 -
             0.3534 / (0.09 + q2 * q2));
 }
 
@@ -254,7 +251,7 @@ struct PhotoKinematics {   // per-(K,q) quantities of dcs.hh:372-387 and 340-342
     double centre, width, E, y, Mq;
 };
 
-NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm::Tables &T,
+NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm::Tab &T,
                                PhotoKinematics &k) {
     if ((q < 1.) || (q < 2E-03 * K)) return false;            // dcs.hh:357-359
     const double M = 0.931494;
@@ -265,8 +262,8 @@ NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm:
     const double Q2min = p.n_m2 * y * y / (1 - y);
     const double Q2max = 2.0 * M * (q - mpi) - mpi * mpi;
     if ((Q2max < Q2min) | (Q2min < 0)) return false;
-    const double lo = glibm::log(Q2min, T.log_tab);
-    const double hi = glibm::log(Q2max, T.log_tab);
+    const double lo = glibm::log(Q2min, T);
+    const double hi = glibm::log(Q2max, T);
     k.width = hi - lo;
     k.centre = 0.5 * (hi + lo);
     k.E = E;
@@ -277,9 +274,9 @@ NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm:
 
 // d2sigma/dq dQ2 * Q2 at node t in [-1,1] (dcs.hh:335-355, 397-402)
 NOA_HD double photonuclear_node(double t, double q, const PhotoKinematics &k, const Params &p,
-                                const glibm::Tables &T) {
+                                const glibm::Tab &T) {
     const double cf = 2.603096E-35;
-    const double Q2 = glibm::exp(k.centre + 0.5 * k.width * t, T.exp_tab);
+    const double Q2 = glibm::exp(k.centre + 0.5 * k.width * t, T);
     const double E = k.E;
     const double y = k.y;
     const double x = 0.5 * Q2 / k.Mq;
@@ -296,7 +293,7 @@ NOA_HD double photonuclear_finish(double K, double ds, const PhotoKinematics &k,
     return (ds < 0.) ? 0. : 0.5 * ds * k.width * 1E+03 * kAvogadro * (p.mass + K) / p.A;
 }
 
-NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tables &T) {
+NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab &T) {
     PhotoKinematics k;
     if (!photonuclear_setup(K, q, p, T, k)) return 0.;
     double acc = 0.;
@@ -309,7 +306,7 @@ NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab
 // ------------------------------------------------------------------------------------------
 // Ionisation -- src/noa/pms/dcs.hh:408-443
 // ------------------------------------------------------------------------------------------
-NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tables &T) {
+NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &T) {
     const double me = kElectronMass;
     const double P2 = K * (K + 2. * p.mass);
     const double E = K + p.mass;
@@ -322,16 +319,16 @@ NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Table
     const double cs = 1.535336E-05 * E * p.Zd / p.A * (a0 + 1. / q * (a1 + a2 / q));
     double Delta = 0.;
     if (K >= p.i_kthr) {
-        const double L1 = glibm::log(1. + 2. * q / me, T.log_tab);
+        const double L1 = glibm::log(1. + 2. * q / me, T);
         Delta = 1.16141E-03 * L1 *
-                (glibm::log(4. * E * (E - q) / p.i_m2, T.log_tab) - L1);
+                (glibm::log(4. * E * (E - q) / p.i_m2, T) - L1);
     }
     return cs * (1. + Delta);
 }
 
 // Closed-form ionisation integrals (dcs.hh:446-496); integrand 0 = DEL, 1 = CEL
 NOA_HD double ionisation_closed_form(double K, double xlow, int integrand, const Params &p,
-                                     const glibm::Tables &T) {
+                                     const glibm::Tab &T) {
     const double me = kElectronMass;
     const double P2 = K * (K + 2. * p.mass);
     const double E = K + p.mass;
@@ -344,16 +341,16 @@ NOA_HD double ionisation_closed_form(double K, double xlow, int integrand, const
     const double a0 = 0.5 / P2, a1 = -1. / Wmax, a2 = E * E / P2;
     double term;
     if (integrand == 0)
-        term = a0 * (Wmax - Wmin) + a1 * glibm::log(Wmax / Wmin, T.log_tab) +
+        term = a0 * (Wmax - Wmin) + a1 * glibm::log(Wmax / Wmin, T) +
                a2 * (1. / Wmin - 1. / Wmax);
     else
         term = 0.5 * a0 * (Wmax * Wmax - Wmin * Wmin) + a1 * (Wmax - Wmin) +
-               a2 * glibm::log(Wmax / Wmin, T.log_tab);
+               a2 * glibm::log(Wmax / Wmin, T);
     return 1.535336E-05 * p.Zd / p.A * term;
 }
 
 template <int PROCESS>
-NOA_HD double dcs_eval(double K, double q, const Params &p, const glibm::Tables &T) {
+NOA_HD double dcs_eval(double K, double q, const Params &p, const glibm::Tab &T) {
     if (PROCESS == 0) return bremsstrahlung(K, q, p, T);
     if (PROCESS == 1) return pair_production(K, q, p, T);
     if (PROCESS == 2) return photonuclear(K, q, p, T);
