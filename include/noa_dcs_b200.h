@@ -22,6 +22,9 @@
  *                                                                   955-1001
  *   noa_dcs_table_f64          the eight such columns (4 processes x DEL, CEL) of one element in
  *                              one launch, one DCS evaluation per node feeding both integrands
+ *   noa_dcs_table_scatter_f64  the same for a cyclic shard of the energies, finished rows written
+ *                              straight into every GPU's table over NVLink (no reference
+ *                              counterpart: the reference is single-process)
  *   noa_dcs_vmap_host_f64      dcs::map(f) on CPU tensors           src/noa/pms/dcs.hh:50-60
  *                              (host buffers in, host buffers out; copies pipelined with compute)
  */
@@ -44,6 +47,7 @@ extern "C" {
 #define NOA_DCS_NPROCESS 4
 
 #define NOA_DCS_MAX_ELEMENTS 8 /* elements per material in noa_dcs_vmap_mixture_f64 */
+#define NOA_DCS_MAX_PEERS 16   /* destination tables in noa_dcs_table_scatter_f64 */
 
 /* negative error codes (positive ones are cudaError_t) */
 #define NOA_DCS_EINVAL (-1)  /* bad process id / mask / count / null pointer */
@@ -94,6 +98,22 @@ int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double
                       double *cel, void *stream);
 
 /*
+ * Multi-GPU form of noa_dcs_table_f64: builds the rows of the energies K_local[0 .. n_local) and
+ * stores each finished value into n_peers destination tables at once -- this GPU's own and every
+ * peer's, the latter mapped into this process (CUDA IPC / symmetric memory) and written over
+ * NVLink from inside the table kernel, so the build and the "all-gather" are one launch.
+ * Local row r is row first_row + r * row_stride of the [4][n_total] destination tables
+ * (cyclic partition: first_row = rank, row_stride = world).  peer_del / peer_cel are HOST arrays of
+ * n_peers device pointers.  The caller synchronises the ranks afterwards (a barrier over the same
+ * stream); remote stores are followed by a system-scope fence.
+ */
+int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int64_t n_local,
+                              double xlow, int32_t min_points, double A, double I, int32_t Z,
+                              double mass, int32_t n_peers, double *const *peer_del,
+                              double *const *peer_cel, int64_t n_total, int64_t first_row,
+                              int64_t row_stride, void *stream);
+
+/*
  * One column of the above, with the reference's own call shape
  *   dcs::vmap_integral(dcs::recoil_integral(f_process, integrand))(result, K, xlow, element, mass,
  *                                                                  min_points)
@@ -123,6 +143,12 @@ int noa_dcs_vmap_host_f64(noa_dcs_stager *stager, int process, const double *h_K
  * peak that the rooflines are quoted against.  Executes blocks * threads * iters * 16 DFMA.
  */
 int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink, void *stream);
+
+/* Same loop with other operand shapes, to measure what register-file bandwidth allows:
+ * mode 0 = the probe above (DFMA, one register-pair source), 1 = DFMA with three distinct
+ * register-pair sources, 2 = DFMA with two, 3 = DADD, 4 = DMUL. */
+int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t threads,
+                            double *sink, void *stream);
 
 /* Lane mapping of the pair-production kernel: 0 = one pair per thread (default), 1 = one
  * Gauss-Legendre node per lane (8 lanes per pair, shuffle gather).  Same results either way. */

@@ -191,6 +191,18 @@ vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
 // ------------------------------------------------------------------------------------------
 constexpr int kTableChunk = 1536;   // node terms staged per pass: 2 x 12 KB of shared memory
 
+// Where the finished rows go: `n_peers` destination tables (this GPU's own and, in the multi-GPU
+// build, every peer's, mapped over NVLink), each [4][n_total]; local row r is global row
+// first_row + r * row_stride.
+struct TableOut {
+    int32_t n_peers;
+    int64_t n_total;
+    int64_t first_row;
+    int64_t row_stride;
+    double *del[NOA_DCS_MAX_PEERS];
+    double *cel[NOA_DCS_MAX_PEERS];
+};
+
 struct TablePlan {
     int32_t n_slots;          // processes to build
     int32_t process[4];       // heaviest first, so the tail of the grid is cheap rows
@@ -200,9 +212,8 @@ struct TablePlan {
 };
 
 __global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
-table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
-             double *__restrict__ cel, const __grid_constant__ TablePlan plan,
-             const __grid_constant__ Params p) {
+table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
+             const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
     __shared__ glibm::Tables s_tables;
     __shared__ double s_del[kTableChunk];
     __shared__ double s_cel[kTableChunk];
@@ -214,10 +225,18 @@ table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
     const double k = K[row];
     const int tid = threadIdx.x;
 
+    // destination index and the lane that owns each integrand (lane 0: DEL, lane 32: CEL)
+    const int64_t at = (int64_t) plan.out_row[process] * out.n_total + out.first_row +
+                       row * out.row_stride;
+    double *const *dst = (tid == 0) ? out.del : out.cel;
+    const bool writer = (tid == 0 || tid == 32) && dst[0] != nullptr;
+
     if (process == 3 && k <= p.i_kthr) {          // dcs.hh:963-966, 987-990
-        const int64_t at = (int64_t) plan.out_row[3] * nK + row;
-        if (tid == 0 && del) del[at] = ionisation_closed_form(k, plan.xlow, 0, p, T);
-        if (tid == 32 && cel) cel[at] = ionisation_closed_form(k, plan.xlow, 1, p, T);
+        if (writer) {
+            const double v = ionisation_closed_form(k, plan.xlow, tid == 0 ? 0 : 1, p, T);
+            for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
+            if (out.n_peers > 1) __threadfence_system();
+        }
         return;
     }
 
@@ -247,22 +266,42 @@ table_kernel(const double *__restrict__ K, int64_t nK, double *__restrict__ del,
         }
         __syncthreads();
     }
-    const int64_t at = (int64_t) plan.out_row[process] * nK + row;
-    if (tid == 0 && del) del[at] = acc / (k + p.mass);
-    if (tid == 32 && cel) cel[at] = acc / (k + p.mass);
+    if (writer) {
+        const double v = acc / (k + p.mass);
+        // one store per destination: the local table and, over NVLink, each peer's copy
+        for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
+        if (out.n_peers > 1) __threadfence_system();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// FP64 peak probe: 16 independent DFMA chains per thread
+// FP64 peak probe: 16 independent chains per thread.
+//   mode 0  DFMA a = a * const + const     (1 register-pair source)  -> the roofline denominator
+//   mode 1  DFMA a = a * b + c             (3 distinct register-pair sources)
+//   mode 2  DFMA a = a * b + const         (2 register-pair sources)
+//   mode 3  DADD a = a + b,  mode 4  DMUL a = a * b
+// Modes 1-4 exist to measure how register-file bandwidth limits real instruction mixes.
 // ------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void fp64_probe_kernel(int64_t iters, double *sink) {
-    double a[16];
+    double a[16], b[4], c[4];
 #pragma unroll
     for (int j = 0; j < 16; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
-    const double b = 0.999999, c = 1e-6;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        b[j] = 0.999999 + 1e-9 * (threadIdx.x + j);
+        c[j] = 1e-6 + 1e-12 * (threadIdx.x + j);
+    }
+    const double kb = 0.999999, kc = 1e-6;
     for (int64_t it = 0; it < iters; it++) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = fma(a[j], b, c);
+        for (int j = 0; j < 16; j++) {
+            if (MODE == 0) a[j] = fma(a[j], kb, kc);
+            if (MODE == 1) a[j] = fma(a[j], b[j & 3], c[(j >> 2) & 3]);
+            if (MODE == 2) a[j] = fma(a[j], b[j & 3], kc);
+            if (MODE == 3) a[j] = __dadd_rn(a[j], c[j & 3]);
+            if (MODE == 4) a[j] = __dmul_rn(a[j], b[j & 3]);
+        }
     }
     double s = 0.;
 #pragma unroll
@@ -464,10 +503,10 @@ int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const doubl
 
 static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
                       double xlow, int32_t min_points, double A, double I, int32_t Z, double mass,
-                      double *del, double *cel, void *stream) {
+                      const TableOut &out, void *stream) {
     if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1)
         return NOA_DCS_EINVAL;
-    if (nK == 0 || (!del && !cel)) return 0;
+    if (nK == 0 || (!out.del[0] && !out.cel[0])) return 0;
     if (!K) return NOA_DCS_EINVAL;
     TablePlan plan{};
     for (int i = 0; i < 4; i++) plan.out_row[i] = single_row ? 0 : i;
@@ -483,15 +522,48 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
     int rc = device_info(info);
     if (rc) return rc;
     const Params p = make_params(A, I, Z, mass);
-    table_kernel<<<(unsigned) blocks, kThreads, 0, (cudaStream_t) stream>>>(K, nK, del, cel, plan,
-                                                                           p);
+    table_kernel<<<(unsigned) blocks, kThreads, 0, (cudaStream_t) stream>>>(K, nK, out, plan, p);
     return after_launch();
+}
+
+static TableOut local_out(double *del, double *cel, int64_t nK) {
+    TableOut out{};
+    out.n_peers = 1;
+    out.n_total = nK;
+    out.first_row = 0;
+    out.row_stride = 1;
+    out.del[0] = del;
+    out.cel[0] = cel;
+    return out;
 }
 
 int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
                       int32_t min_points, double A, double I, int32_t Z, double mass, double *del,
                       double *cel, void *stream) {
-    return table_impl(process_mask, false, K, nK, xlow, min_points, A, I, Z, mass, del, cel,
+    return table_impl(process_mask, false, K, nK, xlow, min_points, A, I, Z, mass,
+                      local_out(del, cel, nK), stream);
+}
+
+int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int64_t n_local,
+                              double xlow, int32_t min_points, double A, double I, int32_t Z,
+                              double mass, int32_t n_peers, double *const *peer_del,
+                              double *const *peer_cel, int64_t n_total, int64_t first_row,
+                              int64_t row_stride, void *stream) {
+    if (n_peers < 1 || n_peers > NOA_DCS_MAX_PEERS || !peer_del || !peer_cel)
+        return NOA_DCS_EINVAL;
+    if (n_total < 0 || first_row < 0 || row_stride < 1) return NOA_DCS_EINVAL;
+    if (n_local > 0 && first_row + (n_local - 1) * row_stride >= n_total) return NOA_DCS_ERANGE;
+    TableOut out{};
+    out.n_peers = n_peers;
+    out.n_total = n_total;
+    out.first_row = first_row;
+    out.row_stride = row_stride;
+    for (int j = 0; j < n_peers; j++) {
+        if (!peer_del[j] || !peer_cel[j]) return NOA_DCS_EINVAL;
+        out.del[j] = peer_del[j];
+        out.cel[j] = peer_cel[j];
+    }
+    return table_impl(process_mask, false, K_local, n_local, xlow, min_points, A, I, Z, mass, out,
                       stream);
 }
 
@@ -502,7 +574,9 @@ int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, doubl
         return NOA_DCS_EINVAL;
     if (n > 0 && !result) return NOA_DCS_EINVAL;
     return table_impl(1u << process, true, K, n, xlow, min_points, A, I, Z, mass,
-                      integrand == 0 ? result : nullptr, integrand == 1 ? result : nullptr, stream);
+                      local_out(integrand == 0 ? result : nullptr,
+                                integrand == 1 ? result : nullptr, n),
+                      stream);
 }
 
 int noa_dcs_stager_create(noa_dcs_stager **out, int64_t chunk_pairs, int32_t n_slots) {
@@ -596,7 +670,22 @@ int noa_dcs_vmap_host_f64(noa_dcs_stager *st, int process, const double *h_K, co
 int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink,
                        void *stream) {
     if (iters < 1 || blocks < 1 || threads < 1 || threads > 1024 || !sink) return NOA_DCS_EINVAL;
-    fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>>(iters, sink);
+    fp64_probe_kernel<0><<<blocks, threads, 0, (cudaStream_t) stream>>>(iters, sink);
+    return after_launch();
+}
+
+int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t threads,
+                            double *sink, void *stream) {
+    if (iters < 1 || blocks < 1 || threads < 1 || threads > 1024 || !sink) return NOA_DCS_EINVAL;
+    cudaStream_t s = (cudaStream_t) stream;
+    switch (mode) {
+        case 0: fp64_probe_kernel<0><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 1: fp64_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 2: fp64_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 3: fp64_probe_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 4: fp64_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
+        default: return NOA_DCS_EINVAL;
+    }
     return after_launch();
 }
 

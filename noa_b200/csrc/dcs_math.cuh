@@ -39,6 +39,15 @@ struct Params {
     double i_wmin, i_kthr, i_m2;
 };
 
+// Unroll factor of the in-thread node loops (1 = rolled).  The rolled form keeps the integrand
+// instantiated once; see DESIGN.md for the measured choice.
+#ifndef NOA_NODE_UNROLL
+#define NOA_NODE_UNROLL 1
+#endif
+#define NOA_PRAGMA_(x) _Pragma(#x)
+#define NOA_UNROLL_(n) NOA_PRAGMA_(unroll n)
+#define NOA_NODE_LOOP NOA_UNROLL_(NOA_NODE_UNROLL)
+
 // ---- quadrature rules (src/noa/utils/numerics.hh:97-100, 116-121, 137-144) -------------------
 #define NOA_GL6_X {0.03376524, 0.16939531, 0.38069041, 0.61930959, 0.83060469, 0.96623476}
 #define NOA_GL6_W {0.08566225, 0.18038079, 0.23395697, 0.23395697, 0.18038079, 0.08566225}
@@ -191,7 +200,7 @@ NOA_HD double pair_production(double K, double q, const Params &p, const glibm::
     PairKinematics k;
     if (!pair_setup(K, q, p, T, k)) return 0.;
     double acc = 0.;
-#pragma unroll 1
+    NOA_NODE_LOOP
     for (int j = 0; j < 8; j++) acc += pair_node(NOA_GL(8, x, j), q, k, p, T) * NOA_GL(8, w, j);
     return pair_finish(K, q, acc, k, p, T);
 }
@@ -297,7 +306,7 @@ NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab
     PhotoKinematics k;
     if (!photonuclear_setup(K, q, p, T, k)) return 0.;
     double acc = 0.;
-#pragma unroll 1
+    NOA_NODE_LOOP
     for (int j = 0; j < 9; j++)
         acc += photonuclear_node(NOA_GL(9, x, j), q, k, p, T) * NOA_GL(9, w, j);
     return photonuclear_finish(K, acc, k, p);

@@ -66,3 +66,74 @@ class TableBuilder:
         # gathered[r, c, p, l] is row l * W + r of column (c, p)
         full = self.gathered.permute(1, 2, 3, 0).reshape(2, 4, self.rows_per_rank * self.world)
         return full[:, :, :self.n].contiguous()
+
+
+class PeerTableBuilder:
+    """Table build fused with its exchange: ONE kernel launch per rank computes the rank's cyclic
+    share of the rows and stores every finished value straight into the [2, 4, n_K] table of EVERY
+    rank -- its own and, over NVLink, each peer's (buffers from torch symmetric memory, i.e. CUDA
+    IPC-mapped peer allocations) -- followed by a device-side barrier.  No NCCL collective, no
+    staging copy, no un-permute.  C ABI: noa_dcs_table_scatter_f64.
+
+    Needs NCCL process group + peer access between the GPUs of the box; `make_table_builder`
+    falls back to the all-gather `TableBuilder` when symmetric memory cannot be set up.
+    """
+
+    def __init__(self, K, rank, world, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._ctypes = ctypes
+        self._lib = _lib
+        self.lib = _lib.require_device()
+        self.n = K.numel()
+        self.rank, self.world = rank, world
+        rows = cyclic_rows(self.n, rank, world).to(K.device)
+        self.n_local = rows.numel()
+        self.K_local = K.reshape(-1)[rows].contiguous()
+        group = dist.group.WORLD if group is None else group
+        self.table = symm_mem.empty((2, 4, self.n), dtype=torch.float64, device=K.device)
+        self.table.zero_()
+        self.handle = symm_mem.rendezvous(self.table, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(ptrs) == world
+        half = 4 * self.n * 8
+        self._del = (ctypes.c_void_p * world)(*ptrs)
+        self._cel = (ctypes.c_void_p * world)(*[p + half for p in ptrs])
+        torch.cuda.synchronize(K.device)
+        self.handle.barrier(channel=0)
+
+    def build(self, xlow, element, mass, min_points, processes=None):
+        """Returns the full table [2, 4, n_K] (this rank's symmetric buffer; identical on every rank
+        once the call's trailing barrier has run on the stream)."""
+        mask = 0xF
+        if processes is not None:
+            mask = 0
+            for pr in processes:
+                mask |= 1 << pr.index
+        A, I, Z = element
+        c = self._ctypes
+        dev = self.K_local.device
+        with torch.cuda.device(dev):
+            # peers must be done reading the previous table before anyone overwrites it
+            self.handle.barrier(channel=0)
+            if self.n_local:
+                self._lib.check(self.lib.noa_dcs_table_scatter_f64(
+                    mask, c.c_void_p(self.K_local.data_ptr()), self.n_local, float(xlow),
+                    int(min_points), float(A), float(I), int(Z), float(mass), self.world,
+                    self._del, self._cel, self.n, self.rank, self.world,
+                    c.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            # every rank's rows have landed everywhere once all ranks pass this barrier
+            self.handle.barrier(channel=0)
+        return self.table
+
+
+def make_table_builder(K, rank=0, world=1, group=None, prefer_peer=True):
+    """PeerTableBuilder when `world` > 1 and symmetric memory works, else TableBuilder."""
+    if world > 1 and prefer_peer and K.is_cuda:
+        try:
+            return PeerTableBuilder(K, rank, world, group)
+        except Exception as exc:   # no peer access / symmetric memory unavailable
+            import warnings
+            warnings.warn(f"peer-memory table build unavailable ({exc!r}); using NCCL all-gather")
+    return TableBuilder(K, rank, world, group=group)
