@@ -25,6 +25,7 @@
  *   noa_dcs_table_scatter_f64  the same for a cyclic shard of the energies, finished rows written
  *                              straight into every GPU's table over NVLink (no reference
  *                              counterpart: the reference is single-process)
+ *   noa_dcs_table_exchange_f64 the same plus the rank barrier, all in one kernel launch
  *   noa_dcs_vmap_host_f64      dcs::map(f) on CPU tensors           src/noa/pms/dcs.hh:50-60
  *                              (host buffers in, host buffers out; copies pipelined with compute)
  */
@@ -114,6 +115,26 @@ int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int6
                               int64_t row_stride, void *stream);
 
 /*
+ * noa_dcs_table_scatter_f64 with the rank synchronisation inside the same kernel: after its last
+ * row is stored and fenced, the launch writes `epoch` into slot `my_peer` of every peer's flag
+ * array (peer_flags[j] = peer j's array of n_peers 32-bit words, mapped here like the tables) and
+ * returns only when all n_peers slots of its own array have reached `epoch`, i.e. when every
+ * peer's rows have landed in this GPU's table.  One launch per rank builds, exchanges and
+ * synchronises; work enqueued after it on `stream` sees the complete table.  `epoch` must increase
+ * by one per call on all ranks (flags start at 0, first epoch 1); callers alternate between two
+ * destination tables so a fast rank never overwrites rows a slow rank is still reading.
+ * `done` = four zero-initialised 32-bit words on this device {CTA counter, timeout count, row
+ * queue, reserved}; the second becomes non-zero if a peer did not arrive within about four seconds.
+ */
+int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int64_t n_local,
+                               double xlow, int32_t min_points, double A, double I, int32_t Z,
+                               double mass, int32_t n_peers, int32_t my_peer,
+                               double *const *peer_del, double *const *peer_cel,
+                               uint32_t *const *peer_flags, uint32_t *done, uint32_t epoch,
+                               int64_t n_total, int64_t first_row, int64_t row_stride,
+                               void *stream);
+
+/*
  * One column of the above, with the reference's own call shape
  *   dcs::vmap_integral(dcs::recoil_integral(f_process, integrand))(result, K, xlow, element, mass,
  *                                                                  min_points)
@@ -153,6 +174,12 @@ int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t
 /* Lane mapping of the pair-production kernel: 0 = one pair per thread (default), 1 = one
  * Gauss-Legendre node per lane (8 lanes per pair, shuffle gather).  Same results either way. */
 int noa_dcs_set_pair_mode(int mode);
+
+/* How noa_dcs_table_exchange_f64 runs (measurement hook): 3 = persistent CTAs pulling rows from a
+ * device-side queue, one system fence per CTA (default); 0 / 1 / 2 = one CTA per row with the fence
+ * after every writer lane's stores / once per CTA after the barrier / in the last CTA only (the
+ * last one is for timing experiments: not a sufficient ordering). */
+int noa_dcs_set_exchange_fence_mode(int mode);
 
 /* Launch geometry the element-wise kernels use on the current device (for reporting). */
 int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t *sm_count);

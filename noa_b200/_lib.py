@@ -34,6 +34,10 @@ SIGNATURES = {
     "noa_dcs_table_scatter_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
                                                  _i32, _f64, _i32, ctypes.POINTER(_vp),
                                                  ctypes.POINTER(_vp), _i64, _i64, _i64, _vp]),
+    "noa_dcs_table_exchange_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
+                                                  _i32, _f64, _i32, _i32, ctypes.POINTER(_vp),
+                                                  ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp,
+                                                  ctypes.c_uint32, _i64, _i64, _i64, _vp]),
     "noa_dcs_vmap_integral_f64": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64, _f64,
                                                  _i32, _f64, _f64, _i32, _f64, _vp]),
     "noa_dcs_stager_create": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i32]),
@@ -43,6 +47,7 @@ SIGNATURES = {
     "noa_dcs_fp64_probe": (ctypes.c_int, [_i64, _i32, _i32, _vp, _vp]),
     "noa_dcs_fp64_probe_mode": (ctypes.c_int, [_i32, _i64, _i32, _i32, _vp, _vp]),
     "noa_dcs_set_pair_mode": (ctypes.c_int, [ctypes.c_int]),
+    "noa_dcs_set_exchange_fence_mode": (ctypes.c_int, [ctypes.c_int]),
     "noa_dcs_launch_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_i32),
                                            ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "noa_dcs_launch_count": (_i64, []),

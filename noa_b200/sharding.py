@@ -21,6 +21,20 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def sweep_segments(n_per_material, n_materials, rank, world):
+    """Shard of a multi-material sweep (BASELINE.json config 5): the (material, pair) index space
+    is flattened material-major and cut into `world` contiguous pieces; returns this rank's piece
+    as [(material index, lo, hi), ...] with [lo, hi) a pair range inside that material."""
+    lo, hi = shard_range(n_per_material * n_materials, rank, world)
+    out = []
+    while lo < hi:
+        m, off = divmod(lo, n_per_material)
+        end = min(hi, (m + 1) * n_per_material)
+        out.append((m, off, off + (end - lo)))
+        lo = end
+    return out
+
+
 def cyclic_rows(n, rank, world):
     """Indices rank, rank + W, rank + 2W, ... < n."""
     return torch.arange(rank, max(n, rank), world)
@@ -69,17 +83,28 @@ class TableBuilder:
 
 
 class PeerTableBuilder:
-    """Table build fused with its exchange: ONE kernel launch per rank computes the rank's cyclic
-    share of the rows and stores every finished value straight into the [2, 4, n_K] table of EVERY
-    rank -- its own and, over NVLink, each peer's (buffers from torch symmetric memory, i.e. CUDA
-    IPC-mapped peer allocations) -- followed by a device-side barrier.  No NCCL collective, no
-    staging copy, no un-permute.  C ABI: noa_dcs_table_scatter_f64.
+    """Table build fused with its exchange AND the rank barrier: ONE kernel launch per rank computes
+    the rank's cyclic share of the rows, stores every finished value straight into the
+    [2, 4, n_K] table of EVERY rank -- its own and, over NVLink, each peer's (buffers from torch
+    symmetric memory, i.e. CUDA IPC-mapped peer allocations) -- then publishes an epoch flag to
+    every peer and waits for theirs inside the same kernel.  No NCCL collective, no staging copy,
+    no un-permute, no barrier launch.  C ABI: noa_dcs_table_exchange_f64.
 
-    Needs NCCL process group + peer access between the GPUs of the box; `make_table_builder`
+    Two destination tables alternate (epoch parity): a rank can start build e+1 while a slower
+    peer still reads table e, and build e+2 cannot start anywhere before every rank has finished
+    launching e+1 behind its reads of table e (stream order).  `build()` therefore returns a view
+    that stays valid until the second-next `build()` on the same stream.
+
+    `fused_barrier=False` keeps the older two-step form (noa_dcs_table_scatter_f64 followed by a
+    symmetric-memory barrier kernel) for comparison.
+
+    Needs an NCCL process group + peer access between the GPUs of the box; `make_table_builder`
     falls back to the all-gather `TableBuilder` when symmetric memory cannot be set up.
     """
 
-    def __init__(self, K, rank, world, group=None):
+    FLAG_WORDS = 16     # NOA_DCS_MAX_PEERS 32-bit epoch slots
+
+    def __init__(self, K, rank, world, group=None, fused_barrier=True):
         import ctypes
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
@@ -88,24 +113,33 @@ class PeerTableBuilder:
         self.lib = _lib.require_device()
         self.n = K.numel()
         self.rank, self.world = rank, world
+        self.fused_barrier = fused_barrier
         rows = cyclic_rows(self.n, rank, world).to(K.device)
         self.n_local = rows.numel()
         self.K_local = K.reshape(-1)[rows].contiguous()
         group = dist.group.WORLD if group is None else group
-        self.table = symm_mem.empty((2, 4, self.n), dtype=torch.float64, device=K.device)
-        self.table.zero_()
-        self.handle = symm_mem.rendezvous(self.table, group)
+        per_table = 2 * 4 * self.n
+        # [table 0 | table 1 | flag words] in one symmetric allocation
+        self.buffer = symm_mem.empty((2 * per_table + self.FLAG_WORDS // 2,), dtype=torch.float64,
+                                     device=K.device)
+        self.buffer.zero_()
+        self.tables = [self.buffer[b * per_table:(b + 1) * per_table].view(2, 4, self.n)
+                       for b in range(2)]
+        self.handle = symm_mem.rendezvous(self.buffer, group)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         assert len(ptrs) == world
+        vp = ctypes.c_void_p
         half = 4 * self.n * 8
-        self._del = (ctypes.c_void_p * world)(*ptrs)
-        self._cel = (ctypes.c_void_p * world)(*[p + half for p in ptrs])
+        self._del = [(vp * world)(*[p + b * per_table * 8 for p in ptrs]) for b in range(2)]
+        self._cel = [(vp * world)(*[p + b * per_table * 8 + half for p in ptrs]) for b in range(2)]
+        self._flags = (vp * world)(*[p + 2 * per_table * 8 for p in ptrs])
+        self.done = torch.zeros(4, dtype=torch.int32, device=K.device)
+        self.epoch = 0
         torch.cuda.synchronize(K.device)
-        self.handle.barrier(channel=0)
+        self.handle.barrier(channel=0)     # everyone's buffer is zeroed before anyone writes
 
     def build(self, xlow, element, mass, min_points, processes=None):
-        """Returns the full table [2, 4, n_K] (this rank's symmetric buffer; identical on every rank
-        once the call's trailing barrier has run on the stream)."""
+        """Returns the full table [2, 4, n_K]; complete, in stream order, when the launch retires."""
         mask = 0xF
         if processes is not None:
             mask = 0
@@ -114,18 +148,31 @@ class PeerTableBuilder:
         A, I, Z = element
         c = self._ctypes
         dev = self.K_local.device
+        self.epoch += 1
+        b = self.epoch & 1
         with torch.cuda.device(dev):
-            # peers must be done reading the previous table before anyone overwrites it
-            self.handle.barrier(channel=0)
-            if self.n_local:
-                self._lib.check(self.lib.noa_dcs_table_scatter_f64(
+            stream = c.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if self.fused_barrier:
+                self._lib.check(self.lib.noa_dcs_table_exchange_f64(
                     mask, c.c_void_p(self.K_local.data_ptr()), self.n_local, float(xlow),
-                    int(min_points), float(A), float(I), int(Z), float(mass), self.world,
-                    self._del, self._cel, self.n, self.rank, self.world,
-                    c.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-            # every rank's rows have landed everywhere once all ranks pass this barrier
-            self.handle.barrier(channel=0)
-        return self.table
+                    int(min_points), float(A), float(I), int(Z), float(mass), self.world, self.rank,
+                    self._del[b], self._cel[b], self._flags, c.c_void_p(self.done.data_ptr()),
+                    self.epoch, self.n, self.rank, self.world, stream))
+            else:
+                # peers must be done reading this table before anyone overwrites it
+                self.handle.barrier(channel=0)
+                if self.n_local:
+                    self._lib.check(self.lib.noa_dcs_table_scatter_f64(
+                        mask, c.c_void_p(self.K_local.data_ptr()), self.n_local, float(xlow),
+                        int(min_points), float(A), float(I), int(Z), float(mass), self.world,
+                        self._del[b], self._cel[b], self.n, self.rank, self.world, stream))
+                # every rank's rows have landed everywhere once all ranks pass this barrier
+                self.handle.barrier(channel=0)
+        return self.tables[b]
+
+    def timeouts(self):
+        """Number of exchanges in which a peer failed to arrive (synchronises the device)."""
+        return int(self.done[1].item())
 
 
 def make_table_builder(K, rank=0, world=1, group=None, prefer_peer=True):

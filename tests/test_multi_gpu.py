@@ -43,8 +43,22 @@ def _worker(rank, world, port, n_rows, tmp):
     b = b.clone()
     c = peer.build(0.05, ELEMENTS["rock"], MUON_MASS, 180, processes=(dcs.pair_production,))
     torch.cuda.synchronize()
+    c = c.clone()
+    # the older two-step exchange (scatter kernel + barrier launches) must agree as well
+    two_step = sharding.PeerTableBuilder(K, rank, world, fused_barrier=False) \
+        if kind == "PeerTableBuilder" else peer
+    d = two_step.build(0.05, ELEMENTS["rock"], MUON_MASS, 180).clone()
+    # back-to-back builds with alternating elements: the epoch flags and the two alternating
+    # tables must keep every rank consistent without any host synchronisation in between
+    seq = []
+    for i in range(12):
+        el = ELEMENTS["Pb"] if i % 3 == 1 else ELEMENTS["rock"]
+        seq.append(peer.build(0.05, el, MUON_MASS, 60 + 6 * (i % 2)).clone())
+    torch.cuda.synchronize()
+    timeouts = peer.timeouts() if hasattr(peer, "timeouts") else 0
     np.savez(os.path.join(tmp, f"r{rank}.npz"), gather=a.cpu().numpy(), peer=b.cpu().numpy(),
-             again=c.cpu().numpy(), kind=kind)
+             again=c.cpu().numpy(), two_step=d.cpu().numpy(), kind=kind, timeouts=timeouts,
+             seq=torch.stack(seq).cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,4 +78,10 @@ def test_two_rank_table_build(tmp_path, n_rows):
         assert np.array_equal(got["gather"], want), f"all-gather build differs on rank {r}"
         assert np.array_equal(got["peer"], want), f"{got['kind']} build differs on rank {r}"
         assert np.array_equal(got["again"][:, 1], want[:, 1])
+        assert np.array_equal(got["two_step"], want), f"two-step peer build differs on rank {r}"
+        assert int(got["timeouts"]) == 0
+        for i in range(12):
+            el = ELEMENTS["Pb"] if i % 3 == 1 else ELEMENTS["rock"]
+            di, ci = dcs.cuda.tables(K, 0.05, el, MUON_MASS, 60 + 6 * (i % 2))
+            assert np.array_equal(got["seq"][i], torch.stack((di, ci)).cpu().numpy()), (r, i)
         print("rank", r, "builder:", got["kind"])

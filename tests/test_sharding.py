@@ -29,6 +29,24 @@ def test_shard_range_partitions_exactly():
                 assert sorted(rows.tolist()) == list(range(n))
 
 
+def test_sweep_segments_cover_every_pair_once():
+    from noa_b200.sharding import sweep_segments
+    for n_mat, n_materials in ((16, 4), (10, 3), (1 << 26, 4), (7, 1)):
+        for world in (1, 2, 3, 4, 8):
+            covered = []
+            for r in range(world):
+                segs = sweep_segments(n_mat, n_materials, r, world)
+                for m, lo, hi in segs:
+                    assert 0 <= m < n_materials and 0 <= lo < hi <= n_mat
+                    covered.append((m * n_mat + lo, m * n_mat + hi))
+            covered.sort()
+            assert covered[0][0] == 0 and covered[-1][1] == n_mat * n_materials
+            for a, b in zip(covered, covered[1:]):
+                assert a[1] == b[0]
+    # config 5 at 8 GPUs: half a material per rank
+    assert sweep_segments(1 << 26, 4, 3, 8) == [(1, 1 << 25, 1 << 26)]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
