@@ -493,12 +493,12 @@ def run_extras(torch, dist, dcs, grids, physics, lib, rank, world, distributed, 
 def run_sweep(torch, dcs, grids, physics, sharding, Kt, rank, world, timed):
     """BASELINE.json configs[4]: water, standard rock, iron, lead; 2^26 (K, q) pairs per material
     (2^28 in total), all four processes per pair (per element, mass-fraction mixed for water); the
-    flattened (material, pair) space is cut into contiguous shards, one per rank, outputs stay
-    sharded; plus the DEL/CEL tables (10^4 x 1002 nodes) of the five distinct elements, assembled
+    flattened (material, pair) space is cut into contiguous shards of equal cost (a water pair
+    counts twice), one per rank, outputs stay sharded; plus the DEL/CEL tables (10^4 x 1002 nodes) of the five distinct elements, assembled
     on every rank.  Strong scaling: the total work is fixed."""
     n_mat = 1 << 26
     materials = physics.SWEEP_MATERIALS
-    segs = sharding.sweep_segments(n_mat, len(materials), rank, world)
+    segs = sharding.sweep_segments(n_mat, [len(m.elements) for m in materials], rank, world)
     grids_dev = {}
     for _, lo, hi in segs:
         if (lo, hi) not in grids_dev:

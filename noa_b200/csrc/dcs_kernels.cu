@@ -263,7 +263,12 @@ struct TablePlan {
 __device__ NOA_TABLE_ROW_INLINE void table_row(int64_t b, const double *__restrict__ K, int64_t nK,
                                           const TableOut &out, const TablePlan &plan,
                                           const Params &p, const glibm::Tab &T, double *s_del,
-                                          double *s_cel) {
+                                          double *s_cel, uint32_t *queue = nullptr,
+                                          uint32_t *s_next = nullptr) {
+    // Persistent form only (queue != nullptr): lane 64, idle while lanes 0 / 32 add the node terms
+    // up, pops the CTA's next row at that point -- late enough that a heavy row in flight never
+    // sits on a row another CTA could have started (a pop at row start cost 17 % at 8 GPUs),
+    // early enough that the atomic's round trip is hidden behind the summation.
     const int process = plan.process[b / nK];
     const int64_t row = nK - 1 - (b % nK);
     const double k = K[row];
@@ -280,6 +285,7 @@ __device__ NOA_TABLE_ROW_INLINE void table_row(int64_t b, const double *__restri
             const double v = ionisation_closed_form(k, plan.xlow, tid == 0 ? 0 : 1, p, T);
             for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
         }
+        if (queue != nullptr && tid == 64) *s_next = atomicAdd(queue, 1u);
         return;
     }
 
@@ -306,6 +312,8 @@ __device__ NOA_TABLE_ROW_INLINE void table_row(int64_t b, const double *__restri
             for (uint32_t i = 0; i < count; i++) acc += s_del[i];
         } else if (tid == 32) {
             for (uint32_t i = 0; i < count; i++) acc += s_cel[i];
+        } else if (tid == 64 && queue != nullptr && base + kTableChunk >= total) {
+            *s_next = atomicAdd(queue, 1u);
         }
         __syncthreads();
     }
@@ -344,15 +352,12 @@ table_exchange_kernel(const double *__restrict__ K, int64_t nK, const __grid_con
     __shared__ uint32_t s_item[2];
     const glibm::Tab T = stage_tables(s_tables);
     const uint32_t total = (uint32_t) (nK * plan.n_slots);
-    // the pop of the next row is issued before the current row is computed, so its latency
-    // (an atomic round trip to L2) is off the critical path
-    if (threadIdx.x == 0) s_item[0] = atomicAdd(out.done + 2, 1u);
+    if (threadIdx.x == 64) s_item[0] = atomicAdd(out.done + 2, 1u);
     for (int cur = 0;; cur ^= 1) {
         __syncthreads();                       // s_item[cur] written; node buffers free again
         const uint32_t b = s_item[cur];
         if (b >= total) break;
-        if (threadIdx.x == 0) s_item[cur ^ 1] = atomicAdd(out.done + 2, 1u);
-        table_row(b, K, nK, out, plan, p, T, s_del, s_cel);
+        table_row(b, K, nK, out, plan, p, T, s_del, s_cel, out.done + 2, &s_item[cur ^ 1]);
     }
     table_exchange_tail(out);
 }

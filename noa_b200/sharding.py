@@ -21,17 +21,32 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def sweep_segments(n_per_material, n_materials, rank, world):
-    """Shard of a multi-material sweep (BASELINE.json config 5): the (material, pair) index space
-    is flattened material-major and cut into `world` contiguous pieces; returns this rank's piece
-    as [(material index, lo, hi), ...] with [lo, hi) a pair range inside that material."""
-    lo, hi = shard_range(n_per_material * n_materials, rank, world)
+def sweep_segments(n_per_material, weights, rank, world):
+    """Shard of a multi-material sweep (BASELINE.json config 5).  `weights[m]` is the cost of one
+    pair of material m (its number of elements: water = H + O costs two single-element pairs), or an
+    int meaning that many materials of weight 1.  The (material, pair) space is laid out
+    material-major on a cost axis and cut into `world` contiguous pieces of equal cost; returns this
+    rank's piece as [(material index, lo, hi), ...] with [lo, hi) a pair range inside the material."""
+    if isinstance(weights, int):
+        weights = [1] * weights
+    starts, total = [], 0
+    for w in weights:
+        starts.append(total)
+        total += int(w) * n_per_material
+
+    def locate(cost):                # cost-axis position -> (material, pair)
+        if cost >= total:
+            return len(weights), 0
+        m = max(i for i, s0 in enumerate(starts) if s0 <= cost)
+        return m, (cost - starts[m]) // int(weights[m])
+
+    (m0, p0), (m1, p1) = locate(rank * total // world), locate((rank + 1) * total // world)
     out = []
-    while lo < hi:
-        m, off = divmod(lo, n_per_material)
-        end = min(hi, (m + 1) * n_per_material)
-        out.append((m, off, off + (end - lo)))
-        lo = end
+    for m in range(m0, min(m1, len(weights) - 1) + 1):
+        lo = p0 if m == m0 else 0
+        hi = p1 if m == m1 else n_per_material
+        if lo < hi:
+            out.append((m, lo, hi))
     return out
 
 

@@ -42,6 +42,18 @@ class Checker:
         self._vint.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _dp, ctypes.c_int64,
                                ctypes.c_double, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
                                ctypes.c_int32, ctypes.c_double]
+        i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+        self._coulomb = {}
+        for name, args in (
+                ("coulomb_data", [_dp, _dp, _dp, _dp, _dp, i64, f64, f64, i32, f64]),
+                ("coulomb_transport", [_dp, _dp, _dp, _dp, i64, i64]),
+                ("hard_scattering", [_dp, _dp, _dp, _dp, _dp, _dp, _dp, i32, i32]),
+                ("soft_scattering", [_dp, _dp, i64, f64, f64, i32, f64])):
+            fn = getattr(lib, pre + name, None)     # absent in an oracle/_ref built before they existed
+            if fn is not None:
+                fn.restype = ctypes.c_int
+                fn.argtypes = args
+                self._coulomb[name] = fn
         thr = getattr(lib, "oracle_max_threads" if kind == "port" else "noa_ref_threads")
         thr.restype = ctypes.c_int
         self.max_threads = int(thr())
@@ -86,6 +98,50 @@ class Checker:
         return out
 
 
+    # ---- Coulomb / soft scattering (src/noa/pms/dcs.hh:499-952) -----------------------------------
+    def coulomb_data(self, K, element, mass):
+        """dcs::coulomb_data -> (fCM [n,2], screening [n,9], fspin [n], invlambda [n])"""
+        K = _f64(K)
+        n = K.size
+        fcm, scr = np.zeros((n, 2)), np.zeros((n, 9))
+        fspin, invl = np.zeros(n), np.zeros(n)
+        self._coulomb["coulomb_data"](_p(fcm), _p(scr), _p(fspin), _p(invl), _p(K), n,
+                                      float(element[0]), float(element[1]), int(element[2]),
+                                      float(mass))
+        return fcm, scr, fspin, invl
+
+    def coulomb_transport(self, screening, fspin, mu):
+        """dcs::coulomb_transport -> coefficients [n,2]; mu has 1 or n entries"""
+        scr, fspin, mu = _f64(screening), _f64(fspin), _f64(mu)
+        n = fspin.size
+        assert scr.size == 9 * n and mu.size in (1, n)
+        coef = np.zeros((n, 2))
+        self._coulomb["coulomb_transport"](_p(coef), _p(scr), _p(fspin), _p(mu), mu.size, n)
+        return coef
+
+    def hard_scattering(self, G, fcm, screening, invlambda, fspin):
+        """dcs::hard_scattering on [nel, nkin, ...] arrays -> (mu0 [nkin], lb_h [nkin])"""
+        invl = np.ascontiguousarray(np.asarray(invlambda, dtype=np.float64))
+        if invl.ndim == 1:
+            invl = invl[None]
+        nel, nkin = invl.shape
+        G, fcm, scr, fspin = _f64(G), _f64(fcm), _f64(screening), _f64(fspin)
+        assert G.size == 2 * nel * nkin and fcm.size == 2 * nel * nkin
+        assert scr.size == 9 * nel * nkin and fspin.size == nel * nkin
+        mu0, lb_h = np.zeros(nkin), np.zeros(nkin)
+        self._coulomb["hard_scattering"](_p(mu0), _p(lb_h), _p(G), _p(fcm), _p(scr),
+                                         _p(_f64(invl)), _p(fspin), nel, nkin)
+        return mu0, lb_h
+
+    def soft_scattering(self, K, element, mass):
+        """dcs::soft_scattering -> ms1 [n]"""
+        K = _f64(K)
+        out = np.zeros_like(K)
+        self._coulomb["soft_scattering"](_p(out), _p(K), K.size, float(element[0]),
+                                         float(element[1]), int(element[2]), float(mass))
+        return out
+
+
 def _make(target):
     subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
 
@@ -104,8 +160,8 @@ def build_reference(reference_root="/root/reference"):
 
 
 def load_port():
-    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(
-            os.path.join(_HERE, "dcs_oracle.c")):
+    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < max(
+            os.path.getmtime(os.path.join(_HERE, f)) for f in ("dcs_oracle.c", "coulomb_oracle.c")):
         build_port()
     return Checker(ctypes.CDLL(PORT_SO), "port")
 

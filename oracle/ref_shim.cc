@@ -7,6 +7,8 @@
 //   noa::pms::dcs::vmap / pvmap           (src/noa/pms/dcs.hh:35-75)
 //   noa::pms::dcs::vmap_integral          (src/noa/pms/dcs.hh:115-130)
 //   noa::pms::dcs::recoil_integral        (src/noa/pms/dcs.hh:89-105, 955-1001)
+//   noa::pms::dcs::coulomb_data / coulomb_transport / hard_scattering / soft_scattering
+//                                         (src/noa/pms/dcs.hh:600-622, 674-693, 843-872, 940-952)
 // No reference source is copied into this repository; this file only *calls* it.
 #include <noa/pms/dcs.hh>
 
@@ -89,6 +91,46 @@ int noa_ref_vmap_integral(int process, int integrand, int parallel, const double
     }
 #undef NOA_REF_CASE
     return 1;
+}
+
+// ---- Coulomb and soft scattering ------------------------------------
+int noa_ref_coulomb_data(double *fcm, double *screening, double *fspin, double *invlambda,
+                         const double *K, int64_t n, double A, double I, int32_t Z, double mass) {
+    const AtomicElement el{A, I, Z};
+    auto opt = torch::kFloat64;
+    dcs::coulomb_data(torch::from_blob(fcm, {n, 2}, opt), torch::from_blob(screening, {n, 9}, opt),
+                      wrap(fspin, n), wrap(invlambda, n), wrap(K, n), el, mass);
+    return 0;
+}
+
+int noa_ref_coulomb_transport(double *coef, const double *screening, const double *fspin,
+                              const double *mu, int64_t n_mu, int64_t n) {
+    auto opt = torch::kFloat64;
+    dcs::coulomb_transport(torch::from_blob(coef, {n, 2}, opt),
+                           torch::from_blob(const_cast<double *>(screening), {n, 9}, opt),
+                           wrap(fspin, n), wrap(mu, n_mu));
+    return 0;
+}
+
+int noa_ref_hard_scattering(double *mu0, double *lb_h, const double *G, const double *fcm,
+                            const double *screening, const double *invlambda, const double *fspin,
+                            int32_t nel, int32_t nkin) {
+    auto opt = torch::kFloat64;
+    auto c = [](const double *p) { return const_cast<double *>(p); };
+    dcs::hard_scattering(wrap(mu0, nkin), wrap(lb_h, nkin),
+                         torch::from_blob(c(G), {nel, nkin, 2}, opt),
+                         torch::from_blob(c(fcm), {nel, nkin, 2}, opt),
+                         torch::from_blob(c(screening), {nel, nkin, 9}, opt),
+                         torch::from_blob(c(invlambda), {nel, nkin}, opt),
+                         torch::from_blob(c(fspin), {nel, nkin}, opt));
+    return 0;
+}
+
+int noa_ref_soft_scattering(double *ms1, const double *K, int64_t n, double A, double I, int32_t Z,
+                            double mass) {
+    const AtomicElement el{A, I, Z};
+    dcs::soft_scattering(wrap(ms1, n), wrap(K, n), el, mass);
+    return 0;
 }
 
 }  // extern "C"

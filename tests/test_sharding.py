@@ -31,19 +31,23 @@ def test_shard_range_partitions_exactly():
 
 def test_sweep_segments_cover_every_pair_once():
     from noa_b200.sharding import sweep_segments
-    for n_mat, n_materials in ((16, 4), (10, 3), (1 << 26, 4), (7, 1)):
-        for world in (1, 2, 3, 4, 8):
-            covered = []
+    for n_mat, weights in ((16, 4), (10, 3), (1 << 26, [2, 1, 1, 1]), (7, 1), (12, [2, 1, 3])):
+        wl = [1] * weights if isinstance(weights, int) else weights
+        for world in (1, 2, 3, 4, 5, 8):
+            covered, cost = [], []
             for r in range(world):
-                segs = sweep_segments(n_mat, n_materials, r, world)
+                segs = sweep_segments(n_mat, weights, r, world)
                 for m, lo, hi in segs:
-                    assert 0 <= m < n_materials and 0 <= lo < hi <= n_mat
+                    assert 0 <= m < len(wl) and 0 <= lo < hi <= n_mat
                     covered.append((m * n_mat + lo, m * n_mat + hi))
+                cost.append(sum(wl[m] * (hi - lo) for m, lo, hi in segs))
             covered.sort()
-            assert covered[0][0] == 0 and covered[-1][1] == n_mat * n_materials
+            assert covered[0][0] == 0 and covered[-1][1] == n_mat * len(wl)
             for a, b in zip(covered, covered[1:]):
                 assert a[1] == b[0]
-    # config 5 at 8 GPUs: half a material per rank
+            assert max(cost) - min(cost) <= 2 * max(wl)       # equal cost up to rounding
+    # config 5 at 8 GPUs: 5 cost units of 2^26 over 8 ranks; rank 0 starts inside water
+    assert sweep_segments(1 << 26, [2, 1, 1, 1], 0, 8) == [(0, 0, 5 << 22)]
     assert sweep_segments(1 << 26, 4, 3, 8) == [(1, 1 << 25, 1 << 26)]
 
 

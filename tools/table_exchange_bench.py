@@ -12,6 +12,10 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
 lib = _lib.require_device()
 K = torch.from_numpy(grids.table_energies(10000)).cuda()
+# EMULATE_WORLD=8 on one GPU: the per-rank share of an 8-GPU build (every 8th energy)
+emulate = int(os.environ.get("EMULATE_WORLD", "1"))
+if emulate > 1:
+    K = K[::emulate].contiguous()
 mp = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 
 def timed(fn, reps=20, warm=3):
@@ -25,7 +29,7 @@ def timed(fn, reps=20, warm=3):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
-out = {"world": world, "min_points": mp}
+out = {"world": world, "min_points": mp, "rows": K.numel()}
 gather = sharding.TableBuilder(K, rank, world)
 out["local_only_ms"] = timed(lambda: gather.compute(gather.K_local, 0.05, STANDARD_ROCK, MUON_MASS, mp, out=gather.compact))
 out["nccl_all_gather_ms"] = timed(lambda: gather.build(0.05, STANDARD_ROCK, MUON_MASS, mp))
