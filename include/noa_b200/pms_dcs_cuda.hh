@@ -138,4 +138,25 @@ namespace noa::pms::dcs::cuda {
                        const AtomicElement &element, const ParticleMass &mass,
                        const Index min_points);
 
+    // ---- Coulomb scattering and soft scattering on the GPU: same argument order, shapes and
+    // in-place semantics as the reference's CPU functors dcs::coulomb_data (dcs.hh:600-622),
+    // dcs::coulomb_transport (:674-693), dcs::hard_scattering (:843-872) and dcs::soft_scattering
+    // (:940-952); callers: test/unit/test-dcs-calc.cc:134-178.
+    //   fCM [n, 2], screening [n, 9], fspin [n], invlambda [n], coefficients [n, 2];
+    //   mu: one cutoff (numel 1) or one per energy;
+    //   hard_scattering: coefficients / transform [nel, nkin, 2], screening [nel, nkin, 9],
+    //   invlambdas / fspins [nel, nkin] -> mu0 [nkin], lb_h [nkin].
+    void coulomb_data(const torch::Tensor &fCM, const torch::Tensor &screening,
+                      const torch::Tensor &fspin, const torch::Tensor &invlambda,
+                      const Energies &kinetic_energies, const AtomicElement &element,
+                      const ParticleMass &mass);
+    void coulomb_transport(const torch::Tensor &coefficients, const torch::Tensor &screening,
+                           const torch::Tensor &fspin, const torch::Tensor &mu);
+    void hard_scattering(const torch::Tensor &mu0, const torch::Tensor &lb_h,
+                         const torch::Tensor &coefficients, const torch::Tensor &transform,
+                         const torch::Tensor &screening, const torch::Tensor &invlambdas,
+                         const torch::Tensor &fspins);
+    void soft_scattering(const Calculation &ms1, const Energies &kinetic_energies,
+                         const AtomicElement &element, const ParticleMass &mass);
+
 }  // namespace noa::pms::dcs::cuda

@@ -146,6 +146,37 @@ int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, doubl
                               int32_t Z, double mass, void *stream);
 
 /*
+ * Coulomb scattering and soft scattering -- the rest of the reference's dcs.hh surface
+ * (SURVEY.md 8(f)); same argument meaning and array layouts as the reference's functors, device
+ * pointers, FP64, bit-identical results.
+ *
+ * noa_dcs_coulomb_data_f64       dcs::coulomb_data         src/noa/pms/dcs.hh:600-622
+ *     per energy K[i]: fcm[2 i .. 2 i + 1] (CM Lorentz factors), screening[9 i .. 9 i + 8]
+ *     (3 screening factors + 6 pole-reduction factors, NSF = 9), fspin[i], invlambda[i].
+ * noa_dcs_coulomb_transport_f64  dcs::coulomb_transport    src/noa/pms/dcs.hh:674-693
+ *     coefficients[2 i .. 2 i + 1] from screening, fspin and the angular cutoff mu
+ *     (n_mu = 1: one cutoff for all energies, else n_mu = n).
+ * noa_dcs_hard_scattering_f64    dcs::hard_scattering      src/noa/pms/dcs.hh:843-872
+ *     coefficients, fcm: [nel][nkin][2]; screening: [nel][nkin][9]; invlambda, fspin: [nel][nkin];
+ *     writes the cutoff angle mu0[nkin] (Ridders root, src/noa/utils/numerics.hh:155-218) and the
+ *     hard-scattering mean free path lb_h[nkin].
+ * noa_dcs_soft_scattering_f64    dcs::soft_scattering      src/noa/pms/dcs.hh:940-952
+ *     ms1[i] = transverse transport of the soft ionisation + photonuclear interactions at K[i]
+ *     (the latter a 102-node quadrature of the photonuclear DCS, dcs.hh:901-938).
+ */
+int noa_dcs_coulomb_data_f64(const double *K, int64_t n, double A, double I, int32_t Z, double mass,
+                             double *fcm, double *screening, double *fspin, double *invlambda,
+                             void *stream);
+int noa_dcs_coulomb_transport_f64(const double *screening, const double *fspin, const double *mu,
+                                  int64_t n_mu, int64_t n, double *coefficients, void *stream);
+int noa_dcs_hard_scattering_f64(const double *coefficients, const double *fcm,
+                                const double *screening, const double *invlambda,
+                                const double *fspin, int32_t nel, int64_t nkin, double *mu0,
+                                double *lb_h, void *stream);
+int noa_dcs_soft_scattering_f64(const double *K, int64_t n, double A, double I, int32_t Z,
+                                double mass, double *ms1, void *stream);
+
+/*
  * Host-buffer form of noa_dcs_vmap_f64 (process 0..3) and noa_dcs_vmap_all_f64 (process = 4,
  * h_result holds 4 * n doubles): copies h_K, h_q to the device in chunks, evaluates, copies the
  * result back, the three stages overlapped on separate streams.  Blocks until h_result is

@@ -40,6 +40,12 @@ SIGNATURES = {
                                                   ctypes.c_uint32, _i64, _i64, _i64, _vp]),
     "noa_dcs_vmap_integral_f64": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64, _f64,
                                                  _i32, _f64, _f64, _i32, _f64, _vp]),
+    "noa_dcs_coulomb_data_f64": (ctypes.c_int, [_vp, _i64, _f64, _f64, _i32, _f64, _vp, _vp, _vp,
+                                                _vp, _vp]),
+    "noa_dcs_coulomb_transport_f64": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "noa_dcs_hard_scattering_f64": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp,
+                                                   _vp]),
+    "noa_dcs_soft_scattering_f64": (ctypes.c_int, [_vp, _i64, _f64, _f64, _i32, _f64, _vp, _vp]),
     "noa_dcs_stager_create": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i32]),
     "noa_dcs_stager_destroy": (ctypes.c_int, [_vp]),
     "noa_dcs_vmap_host_f64": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i64, _f64, _f64,

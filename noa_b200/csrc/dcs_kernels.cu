@@ -520,6 +520,8 @@ static int vmap_all_impl(const double *K, const double *q, double *out, int64_t 
 
 }  // namespace noa_b200
 
+#include "coulomb_kernels.cuh"
+
 using namespace noa_b200;
 
 // staging object of noa_dcs_vmap_host_f64

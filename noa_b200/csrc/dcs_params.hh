@@ -7,6 +7,7 @@
 
 #include <cmath>
 
+#include "coulomb_math.cuh"
 #include "dcs_math.cuh"
 
 namespace noa_b200 {
@@ -71,6 +72,47 @@ inline Params make_params(double A, double I, int32_t Z, double mass) {
         p.i_m2 = mass * mass;
     }
     return p;
+}
+
+// (element, mass)-only sub-expressions of the Coulomb / soft-scattering functions
+// (src/noa/pms/dcs.hh:505-520, 548-585, 538, 880-898, 907; src/noa/pms/physics.hh:82-83).
+inline CoulombParams make_coulomb_params(double A, double I, int32_t Z, double mass) {
+    CoulombParams c{};
+    c.mass = mass;
+    c.Zd = (double) Z;
+    c.series_terms = 10 + Z;
+    {   // centre-of-mass frame
+        const double Ma = A * 0.931494;
+        double M2 = mass + Ma;
+        M2 *= M2;
+        double rM2 = mass / Ma;
+        rM2 *= rM2;
+        c.f_Ma = Ma;
+        c.f_M2 = M2;
+        c.f_2Ma = 2. * Ma;
+        c.f_mMa = mass * (mass + Ma);
+        c.f_rM2 = rM2;
+    }
+    {   // screening
+        const double third = 1. / 3;
+        const double A13 = std::pow(A, third);
+        const double R1 = 1.02934 * A13 + 0.435;
+        const double R2 = 2.;
+        c.s_R1sq = R1 * R1;
+        c.s_R2sq = R2 * R2;
+        c.s_ps0 = 5.179587126E-12 * std::pow((double) Z, 2. / 3.);
+        c.s_wentzel = A * 2.54910918E+08;
+    }
+    c.h_max_mu0 = 0.5 * (1. - std::cos(1E+00 * M_PI / 180.));
+    {   // soft scattering
+        const double cs0 = 1.535336E-05 / A;
+        c.t_m2 = mass * mass;
+        c.t_wmin062 = 0.62 * I;
+        c.t_pref = 2. * cs0 * Z;
+        c.t_lb = std::log(1E-06);
+        c.t_h = (0. - c.t_lb) / kSoftCells;
+    }
+    return c;
 }
 
 }  // namespace noa_b200

@@ -51,6 +51,35 @@ inline torch::Tensor water(torch::Tensor kinetic_energies, torch::Tensor recoil_
                                    {0.111894, 0.888106}, MUON_MASS);
 }
 
+// dcs::coulomb_data -> coulomb_transport(mu) -> hard_scattering for standard rock, with the call
+// shapes of test/unit/test-dcs-calc.cc:134-172; returns {fCM, screening, fspin, invlambda, G, mu0,
+// lb_h}
+inline std::vector<torch::Tensor> coulomb_hard_scattering(torch::Tensor kinetic_energies,
+                                                          double mu) {
+    const int64_t nkin = kinetic_energies.numel();
+    const auto opt = kinetic_energies.options();
+    auto fCM = torch::zeros({nkin, 2}, opt);
+    auto screen = torch::zeros({nkin, 9}, opt);
+    auto fspin = torch::zeros_like(kinetic_energies);
+    auto invlambda = torch::zeros_like(kinetic_energies);
+    dcs::cuda::coulomb_data(fCM, screen, fspin, invlambda, kinetic_energies, STANDARD_ROCK,
+                            MUON_MASS);
+    auto G = torch::zeros_like(fCM);
+    dcs::cuda::coulomb_transport(G, screen, fspin, torch::full({1}, mu, opt));
+    const auto lb_h = torch::zeros_like(kinetic_energies);
+    const auto mu0 = torch::zeros_like(kinetic_energies);
+    dcs::cuda::hard_scattering(mu0, lb_h, G.view({1, nkin, 2}), fCM.view({1, nkin, 2}),
+                               screen.view({1, nkin, 9}), invlambda.view({1, nkin}),
+                               fspin.view({1, nkin}));
+    return {fCM, screen, fspin, invlambda, G, mu0, lb_h};
+}
+
+inline torch::Tensor soft_scattering(torch::Tensor kinetic_energies) {
+    const auto result = torch::zeros_like(kinetic_energies);
+    dcs::cuda::soft_scattering(result, kinetic_energies, STANDARD_ROCK, MUON_MASS);
+    return result;
+}
+
 inline void serialise(torch::Tensor tensor, std::string path) { torch::save(tensor, path); }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -70,5 +99,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           "vmap_integral(recoil_integral(process, integrand)) for standard rock");
     m.def("water", &water, py::call_guard<py::gil_scoped_release>(),
           "The four DCS on water (H + O mass-fraction mix), [4, n]");
+    m.def("coulomb_hard_scattering", &coulomb_hard_scattering,
+          py::call_guard<py::gil_scoped_release>(),
+          "coulomb_data + coulomb_transport(mu) + hard_scattering for standard rock");
+    m.def("soft_scattering", &soft_scattering, py::call_guard<py::gil_scoped_release>(),
+          "Soft-scattering transverse transport for standard rock");
     m.def("serialise", &serialise, py::call_guard<py::gil_scoped_release>(), "Save tensor to disk");
 }

@@ -171,4 +171,79 @@ namespace noa::pms::dcs::cuda {
         return result;
     }
 
+    namespace {
+        void check_numel(const torch::Tensor &t, const char *name, int64_t expected) {
+            check_tensor(t, name);
+            TORCH_CHECK(t.numel() == expected, name, " has ", t.numel(), " elements, expected ",
+                        expected);
+        }
+    }  // namespace
+
+    void coulomb_data(const torch::Tensor &fCM, const torch::Tensor &screening,
+                      const torch::Tensor &fspin, const torch::Tensor &invlambda,
+                      const Energies &K, const AtomicElement &el, const ParticleMass &mass) {
+        check_tensor(K, "kinetic_energies");
+        const int64_t n = K.numel();
+        check_numel(fCM, "fCM", 2 * n);
+        check_numel(screening, "screening", 9 * n);
+        check_numel(fspin, "fspin", n);
+        check_numel(invlambda, "invlambda", n);
+        const c10::cuda::CUDAGuard guard(K.device());
+        check_rc(noa_dcs_coulomb_data_f64(K.data_ptr<double>(), n, el.A, el.I, el.Z, mass,
+                                          fCM.data_ptr<double>(), screening.data_ptr<double>(),
+                                          fspin.data_ptr<double>(), invlambda.data_ptr<double>(),
+                                          current_stream(K)),
+                 "noa_dcs_coulomb_data_f64");
+    }
+
+    void coulomb_transport(const torch::Tensor &coefficients, const torch::Tensor &screening,
+                           const torch::Tensor &fspin, const torch::Tensor &mu) {
+        check_tensor(fspin, "fspin");
+        const int64_t n = fspin.numel();
+        check_numel(coefficients, "coefficients", 2 * n);
+        check_numel(screening, "screening", 9 * n);
+        check_tensor(mu, "mu");
+        TORCH_CHECK(mu.numel() == 1 || mu.numel() == n, "mu must hold 1 or ", n, " elements");
+        const c10::cuda::CUDAGuard guard(fspin.device());
+        check_rc(noa_dcs_coulomb_transport_f64(screening.data_ptr<double>(),
+                                               fspin.data_ptr<double>(), mu.data_ptr<double>(),
+                                               mu.numel(), n, coefficients.data_ptr<double>(),
+                                               current_stream(fspin)),
+                 "noa_dcs_coulomb_transport_f64");
+    }
+
+    void hard_scattering(const torch::Tensor &mu0, const torch::Tensor &lb_h,
+                         const torch::Tensor &coefficients, const torch::Tensor &transform,
+                         const torch::Tensor &screening, const torch::Tensor &invlambdas,
+                         const torch::Tensor &fspins) {
+        check_tensor(invlambdas, "invlambdas");
+        TORCH_CHECK(invlambdas.dim() == 2, "invlambdas must be [nel, nkin]");
+        const int64_t nel = invlambdas.size(0), nkin = invlambdas.size(1);
+        check_numel(fspins, "fspins", nel * nkin);
+        check_numel(coefficients, "coefficients", 2 * nel * nkin);
+        check_numel(transform, "transform", 2 * nel * nkin);
+        check_numel(screening, "screening", 9 * nel * nkin);
+        check_numel(mu0, "mu0", nkin);
+        check_numel(lb_h, "lb_h", nkin);
+        const c10::cuda::CUDAGuard guard(invlambdas.device());
+        check_rc(noa_dcs_hard_scattering_f64(coefficients.data_ptr<double>(),
+                                             transform.data_ptr<double>(),
+                                             screening.data_ptr<double>(),
+                                             invlambdas.data_ptr<double>(),
+                                             fspins.data_ptr<double>(), (int32_t) nel, nkin,
+                                             mu0.data_ptr<double>(), lb_h.data_ptr<double>(),
+                                             current_stream(invlambdas)),
+                 "noa_dcs_hard_scattering_f64");
+    }
+
+    void soft_scattering(const Calculation &ms1, const Energies &K, const AtomicElement &el,
+                         const ParticleMass &mass) {
+        check_tensor(K, "kinetic_energies");
+        check_numel(ms1, "ms1", K.numel());
+        const c10::cuda::CUDAGuard guard(K.device());
+        check_rc(noa_dcs_soft_scattering_f64(K.data_ptr<double>(), K.numel(), el.A, el.I, el.Z,
+                                             mass, ms1.data_ptr<double>(), current_stream(K)),
+                 "noa_dcs_soft_scattering_f64");
+    }
+
 }  // namespace noa::pms::dcs::cuda

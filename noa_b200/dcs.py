@@ -176,6 +176,83 @@ def vmap_integral(cs_integral):
     return apply
 
 
+# ---- Coulomb scattering and soft scattering (dcs.hh:499-952) ------------------------------------
+NSF = 9    # physics.hh:86
+
+
+def _numel(t, name, expected):
+    _check_tensor(t, name)
+    if t.numel() != expected:
+        raise ValueError(f"{name} must hold {expected} elements, has {t.numel()}")
+
+
+def coulomb_data(fCM, screening, fspin, invlambda, kinetic_energies, element, mass):
+    """dcs::coulomb_data (dcs.hh:600-622): fills fCM [n, 2], screening [n, 9], fspin [n],
+    invlambda [n] for the energies [n]."""
+    lib = _lib.require_device()
+    _check_tensor(kinetic_energies, "kinetic_energies")
+    n = kinetic_energies.numel()
+    _numel(fCM, "fCM", 2 * n)
+    _numel(screening, "screening", NSF * n)
+    _numel(fspin, "fspin", n)
+    _numel(invlambda, "invlambda", n)
+    A, I, Z = _element(element)
+    with torch.cuda.device(kinetic_energies.device):
+        _lib.check(lib.noa_dcs_coulomb_data_f64(_ptr(kinetic_energies), n, A, I, Z, float(mass),
+                                                _ptr(fCM), _ptr(screening), _ptr(fspin),
+                                                _ptr(invlambda), _stream(kinetic_energies.device)))
+
+
+def coulomb_transport(coefficients, screening, fspin, mu):
+    """dcs::coulomb_transport (dcs.hh:674-693): coefficients [n, 2]; `mu` holds one cutoff for all
+    energies or one per energy."""
+    lib = _lib.require_device()
+    _check_tensor(fspin, "fspin")
+    n = fspin.numel()
+    _numel(coefficients, "coefficients", 2 * n)
+    _numel(screening, "screening", NSF * n)
+    _check_tensor(mu, "mu")
+    if mu.numel() not in (1, n):
+        raise ValueError(f"mu must hold 1 or {n} elements, has {mu.numel()}")
+    with torch.cuda.device(fspin.device):
+        _lib.check(lib.noa_dcs_coulomb_transport_f64(_ptr(screening), _ptr(fspin), _ptr(mu),
+                                                     mu.numel(), n, _ptr(coefficients),
+                                                     _stream(fspin.device)))
+
+
+def hard_scattering(mu0, lb_h, coefficients, transform, screening, invlambdas, fspins):
+    """dcs::hard_scattering (dcs.hh:843-872): invlambdas / fspins [nel, nkin], coefficients /
+    transform [nel, nkin, 2], screening [nel, nkin, 9]; writes mu0 [nkin] and lb_h [nkin]."""
+    lib = _lib.require_device()
+    _check_tensor(invlambdas, "invlambdas")
+    if invlambdas.dim() != 2:
+        raise ValueError("invlambdas must be [nel, nkin]")
+    nel, nkin = invlambdas.shape
+    _numel(fspins, "fspins", nel * nkin)
+    _numel(coefficients, "coefficients", 2 * nel * nkin)
+    _numel(transform, "transform", 2 * nel * nkin)
+    _numel(screening, "screening", NSF * nel * nkin)
+    _numel(mu0, "mu0", nkin)
+    _numel(lb_h, "lb_h", nkin)
+    with torch.cuda.device(invlambdas.device):
+        _lib.check(lib.noa_dcs_hard_scattering_f64(_ptr(coefficients), _ptr(transform),
+                                                   _ptr(screening), _ptr(invlambdas), _ptr(fspins),
+                                                   int(nel), int(nkin), _ptr(mu0), _ptr(lb_h),
+                                                   _stream(invlambdas.device)))
+
+
+def soft_scattering(ms1, kinetic_energies, element, mass):
+    """dcs::soft_scattering (dcs.hh:940-952): ms1[i] for every energy."""
+    lib = _lib.require_device()
+    _check_tensor(kinetic_energies, "kinetic_energies")
+    n = kinetic_energies.numel()
+    _numel(ms1, "ms1", n)
+    A, I, Z = _element(element)
+    with torch.cuda.device(kinetic_energies.device):
+        _lib.check(lib.noa_dcs_soft_scattering_f64(_ptr(kinetic_energies), n, A, I, Z, float(mass),
+                                                   _ptr(ms1), _stream(kinetic_energies.device)))
+
+
 # ---- noa::pms::dcs::cuda ------------------------------------------------------------------------
 class _Cuda:
     """`noa::pms::dcs::cuda` (dcs.hh:1004-1019, src/noa/pms/dcs.cuh:30-51).  The reference has

@@ -13,4 +13,5 @@ if not os.path.exists(os.path.join(_HERE, "_muons.so")):
                       "(or __graft_entry__.build())")
 
 from ._muons import (bremsstrahlung, pair_production, photonuclear, ionisation,  # noqa: E402,F401
-                     all_processes, tables, recoil_integral, water, serialise)
+                     all_processes, tables, recoil_integral, water, serialise,
+                     coulomb_hard_scattering, soft_scattering)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <random>
 
+#include "../noa_b200/csrc/coulomb_math.cuh"
 #include "../noa_b200/csrc/dcs_math.cuh"
 #include "../noa_b200/csrc/dcs_params.hh"
 
@@ -89,6 +90,50 @@ int hostcheck_ionisation_closed_form(int integrand, const double *K, double *out
                                      double xlow, double A, double I, int32_t Z, double mass) {
     const Params p = make_params(A, I, Z, mass);
     for (int64_t i = 0; i < n; i++) out[i] = ionisation_closed_form(K[i], xlow, integrand, p, kT);
+    return 0;
+}
+
+// ---- Coulomb / soft scattering: the kernels' per-energy arithmetic, serial on the host -----------
+int hostcheck_coulomb_data(const double *K, int64_t n, double A, double I, int32_t Z, double mass,
+                           double *fcm, double *screening, double *fspin, double *invlambda) {
+    const CoulombParams c = make_coulomb_params(A, I, Z, mass);
+    for (int64_t i = 0; i < n; i++) {
+        const double k0 = coulomb_frame(K[i], c, fcm[2 * i], fcm[2 * i + 1]);
+        fspin[i] = coulomb_spin(k0, c.mass);
+        invlambda[i] = coulomb_screening(k0, c, kT, screening + kScreenFactors * i);
+    }
+    return 0;
+}
+
+int hostcheck_coulomb_transport(const double *screening, const double *fspin, const double *mu,
+                                int64_t n_mu, int64_t n, double *coef) {
+    for (int64_t i = 0; i < n; i++)
+        coulomb_transport_coefficients(screening + kScreenFactors * i, fspin[i],
+                                       mu[n_mu == 1 ? 0 : i], kT, coef[2 * i], coef[2 * i + 1]);
+    return 0;
+}
+
+int hostcheck_hard_scattering(const double *G, const double *fcm, const double *screening,
+                              const double *invlambda, const double *fspin, int32_t nel,
+                              int64_t nkin, double *mu0, double *lb_h) {
+    const double max_mu0 = make_coulomb_params(1., 1., 1, 1.).h_max_mu0;
+    for (int64_t i = 0; i < nkin; i++) {
+        HardView v{G + 2 * i, fcm + 2 * i, screening + kScreenFactors * i, invlambda + i,
+                   fspin + i, nel, nkin};
+        coulomb_hard_scattering(v, max_mu0, kT, mu0[i], lb_h[i]);
+    }
+    return 0;
+}
+
+int hostcheck_soft_scattering(const double *K, int64_t n, double A, double I, int32_t Z,
+                              double mass, double *ms1) {
+    const Params p = make_params(A, I, Z, mass);
+    const CoulombParams c = make_coulomb_params(A, I, Z, mass);
+    for (int64_t i = 0; i < n; i++) {
+        double acc = 0.;
+        for (int j = 0; j < kSoftNodes; j++) acc += soft_photonuclear_term(j, K[i], p, c, kT);
+        ms1[i] = transverse_transport_ionisation(K[i], p, c, kT) + 2. * acc;
+    }
     return 0;
 }
 

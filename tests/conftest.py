@@ -66,13 +66,17 @@ def hostcheck():
     out = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
     src = os.path.join(ROOT, "oracle", "hostcheck.cc")
     deps = [src] + [os.path.join(ROOT, "noa_b200", "csrc", f)
-                    for f in ("dcs_math.cuh", "dcs_params.hh", "glibm.cuh", "glibm_tables.h")]
+                    for f in ("dcs_math.cuh", "coulomb_math.cuh", "dcs_params.hh", "glibm.cuh",
+                              "glibm_tables.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.run([gxx, "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared",
                         src, "-o", out], check=True)
     lib = ctypes.CDLL(out)
+    for name in ("hostcheck_coulomb_data", "hostcheck_coulomb_transport",
+                 "hostcheck_hard_scattering", "hostcheck_soft_scattering"):
+        getattr(lib, name).restype = ctypes.c_int
     lib.hostcheck_glibm.restype = ctypes.c_int64
     lib.hostcheck_glibm.argtypes = [ctypes.c_int64, ctypes.c_uint64]
     return lib

@@ -10,6 +10,12 @@ Contents (all float64):
   outputs   vmap_<grid>_<element>_<process>           dcs::vmap(f)(...)             4096 / 512 values
             integral_<element>_<process>_<del|cel>_<min_points>   dcs::vmap_integral(recoil_integral)
 Elements: rock (STANDARD_ROCK), H, O, Fe, Pb; muon mass.  xlow = X_FRACTION = 0.05.
+
+A second file, tests/golden/coulomb_golden.npz, holds the Coulomb / soft-scattering functions
+(dcs::coulomb_data, coulomb_transport, hard_scattering, soft_scattering; dcs.hh:499-952) on
+C_K = 256 energies 1e-3..1e6 GeV for the same five elements plus a two-element (water) hard
+scattering case:
+  cd_<el>_{fcm,screen,fspin,invlambda}, ct_<el>_<mu tag>, hs_<el>_{mu0,lbh}, ss_<el>, C_mu_grid
 """
 import os
 import sys
@@ -51,6 +57,38 @@ def main():
                     out[f"integral_{en}_{pn}_{ign}_{mp}"] = ref.vmap_integral(
                         p, ig, out["T_K"], 0.05, mp, ELEMENTS[en], MUON_MASS, threads=8)
     path = os.path.join(ROOT, "tests", "golden", "dcs_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
+    coulomb(ref)
+
+
+MU_CASES = {"one": np.array([1.0]), "small": np.array([1e-3]), "tiny": np.array([1e-12])}
+
+
+def coulomb(ref):
+    out = {}
+    K = grids.table_energies(256, -3.0, 6.0)
+    out["C_K"] = K
+    out["C_mu_grid"] = 10.0 ** np.linspace(-14, 0, K.size)
+    data = {}
+    for en, el in ELEMENTS.items():
+        fcm, scr, fspin, invl = ref.coulomb_data(K, el, MUON_MASS)
+        data[en] = (fcm, scr, fspin, invl)
+        out[f"cd_{en}_fcm"], out[f"cd_{en}_screen"] = fcm, scr
+        out[f"cd_{en}_fspin"], out[f"cd_{en}_invlambda"] = fspin, invl
+        for tag, mu in list(MU_CASES.items()) + [("grid", out["C_mu_grid"])]:
+            out[f"ct_{en}_{tag}"] = ref.coulomb_transport(scr, fspin, mu)
+        mu0, lbh = ref.hard_scattering(out[f"ct_{en}_one"], fcm, scr, invl, fspin)
+        out[f"hs_{en}_mu0"], out[f"hs_{en}_lbh"] = mu0, lbh
+        out[f"ss_{en}"] = ref.soft_scattering(K, el, MUON_MASS)
+    # water: two elements, inverse Wentzel paths weighted by mass fraction
+    w = np.array([0.111894, 0.888106])[:, None]
+    st = lambda i: np.stack((data["H"][i], data["O"][i]))
+    G = np.stack((out["ct_H_one"], out["ct_O_one"]))
+    out["hs_water_invlambda"] = st(3) * w
+    mu0, lbh = ref.hard_scattering(G, st(0), st(1), out["hs_water_invlambda"], st(2))
+    out["hs_water_mu0"], out["hs_water_lbh"] = mu0, lbh
+    path = os.path.join(ROOT, "tests", "golden", "coulomb_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
 
