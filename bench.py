@@ -13,7 +13,8 @@ second, FP64.
              launching stream, barrier + synchronize on both sides, max over ranks.  Inputs rotate
              over 4 distinct buffer sets (384 MB > 126 MB L2) so no step re-reads L2-warm data.
   e2e        the same through the host-buffer entry point (pinned host tensors in, host tensor
-             out; chunked H2D / kernel / D2H pipeline inside the timed region).
+             out): the kernel reads K, q from and writes the result to host memory over PCIe
+             inside the timed region (h2d / d2h bytes are what crosses the link).
   roofline   pair production is FP64-pipe bound (about 3500 FP64-pipe instructions and 24 bytes per
              evaluation): achieved = evals/s x 3500 x 2 flop, peak = the DFMA rate
              measured live by the library's dependent-chain-free probe kernel (the driver's
@@ -216,7 +217,9 @@ def workload_config(n_gpus):
     return {"workload": "pair_production DCS (nested 8-node Gauss-Legendre), standard rock, muon, "
                         "2^22 (K,q) pairs per GPU, synthetic set B (BASELINE.json configs[1])",
             "pairs_per_gpu": N_PAIRS, "element": "standard_rock", "process": "pair_production",
-            "parallelism": f"{n_gpus} independent shard(s), no data-path collective",
+            "parallelism": f"{n_gpus} independent shard(s), no data-path collective; each rank bound "
+                           "to the NUMA node of its GPU" if n_gpus > 1 else
+                           "1 shard, no data-path collective",
             "l2": f"inputs/outputs rotate over {ROTATE} buffer sets "
                   f"({ROTATE * N_PAIRS * 24 >> 20} MiB > 126 MB L2)"}
 
@@ -250,6 +253,8 @@ def main():
                          "(use --impl reference for the CPU reference arm)")
     torch.cuda.set_device(local_rank)
     distributed = world > 1
+    from noa_b200 import sharding as _sharding
+    numa_node = _sharding.bind_to_gpu_numa_node(local_rank) if distributed else None
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -331,7 +336,7 @@ def main():
     value = total * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: pinned host buffers through the host entry point ----------------------------------
-    stager = dcs.HostStager(chunk_pairs=1 << 19, n_slots=4)
+    stager = dcs.HostStager()
     Kh = torch.from_numpy(K0).pin_memory()
     qh = torch.from_numpy(q0).pin_memory()
     outh = torch.empty(N_PAIRS, dtype=torch.float64).pin_memory()
@@ -406,7 +411,8 @@ def main():
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N_PAIRS * 8,
                     "d2h_bytes_per_step": N_PAIRS * 8, "steps": e2e_steps,
-                    "api": "dcs.HostStager.map -> noa_dcs_vmap_host_f64 (pinned host tensors)",
+                    "api": "dcs.HostStager.map -> noa_dcs_vmap_pinned_f64: pinned host tensors read and "
+                           "written in place by the kernel over PCIe, result synchronised",
                     "checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -485,6 +491,39 @@ def run_extras(torch, dist, dcs, grids, physics, lib, rank, world, distributed, 
             "includes": "every rank ends with the full [2,4,n_K] table" if world > 1
             else "single GPU"}
     del builders
+    # the rest of the dcs.hh surface: per-energy, latency-sized launches
+    if rank == 0:
+        n = Kt.numel()
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device="cuda")
+        fCM, screen, fspin, invl, G, mu0, lbh, ms1 = (z(n, 2), z(n, 9), z(n), z(n), z(n, 2), z(n),
+                                                      z(n), z(n))
+        one = torch.ones(1, dtype=torch.float64, device="cuda")
+
+        def coulomb_chain(i):
+            dcs.coulomb_data(fCM, screen, fspin, invl, Kt, physics.STANDARD_ROCK, physics.MUON_MASS)
+            dcs.coulomb_transport(G, screen, fspin, one)
+            dcs.hard_scattering(mu0, lbh, G.view(1, n, 2), fCM.view(1, n, 2), screen.view(1, n, 9),
+                                invl.view(1, n), fspin.view(1, n))
+
+        def local_timed(fn, reps=10, warm=3):
+            for i in range(warm):
+                fn(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for i in range(reps):
+                fn(i)
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        ms = local_timed(coulomb_chain)
+        out["coulomb_data+transport+hard_scattering_1e4"] = {"ms": ms, "energies": n,
+                                                             "launches": 3, "gpus": 1}
+        ms = local_timed(lambda i: dcs.soft_scattering(ms1, Kt, physics.STANDARD_ROCK,
+                                                       physics.MUON_MASS))
+        out["soft_scattering_1e4"] = {"ms": ms, "energies": n, "gpus": 1,
+                                      "photonuclear_evals_per_s": n * 102 / (ms * 1e-3)}
     out["multi_material_sweep_2^28"] = run_sweep(torch, dcs, grids, physics, sharding, Kt, rank,
                                                  world, timed)
     return out

@@ -22,12 +22,15 @@
  *                                                                   955-1001
  *   noa_dcs_table_f64          the eight such columns (4 processes x DEL, CEL) of one element in
  *                              one launch, one DCS evaluation per node feeding both integrands
+ *   noa_dcs_table_material_f64 element tables mixed by mass fraction (PUMAS-style material tables)
  *   noa_dcs_table_scatter_f64  the same for a cyclic shard of the energies, finished rows written
  *                              straight into every GPU's table over NVLink (no reference
  *                              counterpart: the reference is single-process)
  *   noa_dcs_table_exchange_f64 the same plus the rank barrier, all in one kernel launch
  *   noa_dcs_vmap_host_f64      dcs::map(f) on CPU tensors           src/noa/pms/dcs.hh:50-60
  *                              (host buffers in, host buffers out; copies pipelined with compute)
+ *   noa_dcs_vmap_pinned_f64    the same for pinned CPU tensors: one kernel streams the host arrays
+ *                              over PCIe itself, no staging copies at all
  */
 #ifndef NOA_DCS_B200_H
 #define NOA_DCS_B200_H
@@ -97,6 +100,19 @@ int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const doubl
 int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
                       int32_t min_points, double A, double I, int32_t Z, double mass, double *del,
                       double *cel, void *stream);
+
+/*
+ * Tables of a material (mass-fraction mix of elements): table[c][p][i] = sum_e t_e[c][p][i] * w[e]
+ * with t_e the element tables of noa_dcs_table_f64 (c = 0 DEL, 1 CEL), accumulated in composition
+ * order from 0 -- the per-element mixing PUMAS applies to its cross-section and energy-loss
+ * tables (src/noa/3rdparty/_pumas/pumas.c:8054-8078); the reference's own API has single elements
+ * only.  table: [2][4][nK] device doubles; scratch: n_elements x 8 x nK device doubles (the
+ * element tables, left there for the caller).  A, I, Z, w: HOST arrays.  n_elements + 1 launches.
+ */
+int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                               int32_t min_points, int32_t n_elements, const double *A,
+                               const double *I, const int32_t *Z, const double *w, double mass,
+                               double *scratch, double *table, void *stream);
 
 /*
  * Multi-GPU form of noa_dcs_table_f64: builds the rows of the energies K_local[0 .. n_local) and
@@ -191,6 +207,18 @@ int noa_dcs_vmap_host_f64(noa_dcs_stager *stager, int process, const double *h_K
                           int32_t Z, double mass);
 
 /*
+ * The same on PINNED host buffers without any copy calls: h_K, h_q, h_result must be page-locked
+ * and device-addressable (cudaHostAlloc / cudaHostRegister; torch pin_memory() is).  One persistent
+ * kernel reads K / q from host memory over PCIe itself (coalesced loads on the mapped addresses) and
+ * stores the results straight into h_result; reads, arithmetic and writes of the resident warps
+ * overlap inside the kernel.  Asynchronous on `stream`: h_result is complete when the stream has
+ * reached this point (synchronise before reading it).  Returns NOA_DCS_EINVAL for pageable
+ * buffers -- use noa_dcs_vmap_host_f64 for those.
+ */
+int noa_dcs_vmap_pinned_f64(int process, const double *h_K, const double *h_q, double *h_result,
+                            int64_t n, double A, double I, int32_t Z, double mass, void *stream);
+
+/*
  * Measurement helpers (bench.py): a dependent-chain-free DFMA loop used to measure the FP64-pipe
  * peak that the rooflines are quoted against.  Executes blocks * threads * iters * 16 DFMA.
  */
@@ -198,7 +226,11 @@ int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *s
 
 /* Same loop with other operand shapes, to measure what register-file bandwidth allows:
  * mode 0 = the probe above (DFMA, one register-pair source), 1 = DFMA with three distinct
- * register-pair sources, 2 = DFMA with two, 3 = DADD, 4 = DMUL. */
+ * register-pair sources, 2 = DFMA with two, 3 = DADD, 4 = DMUL; 5 / 6 / 7 = mode 0 with one / two /
+ * three independent 32-bit integer multiply-adds issued per DFMA (do non-FP64 instructions issue in
+ * the shadow of the half-rate FP64 dispatch, or do they take issue cycles of their own?);
+ * 10 / 11 / 12 / 13 = 1 / 2 / 4 / 8 dependent DFMA chains per thread (still 16 DFMA per thread and
+ * iteration): with one warp per scheduler the rate gives the dependent-issue latency. */
 int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t threads,
                             double *sink, void *stream);
 

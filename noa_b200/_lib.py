@@ -31,6 +31,10 @@ SIGNATURES = {
                                                 _vp]),
     "noa_dcs_table_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64, _i32,
                                          _f64, _vp, _vp, _vp]),
+    "noa_dcs_table_material_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _i32,
+                                                  ctypes.POINTER(_f64), ctypes.POINTER(_f64),
+                                                  ctypes.POINTER(_i32), ctypes.POINTER(_f64), _f64,
+                                                  _vp, _vp, _vp]),
     "noa_dcs_table_scatter_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
                                                  _i32, _f64, _i32, ctypes.POINTER(_vp),
                                                  ctypes.POINTER(_vp), _i64, _i64, _i64, _vp]),
@@ -50,6 +54,8 @@ SIGNATURES = {
     "noa_dcs_stager_destroy": (ctypes.c_int, [_vp]),
     "noa_dcs_vmap_host_f64": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _i64, _f64, _f64,
                                              _i32, _f64]),
+    "noa_dcs_vmap_pinned_f64": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _i64, _f64, _f64, _i32,
+                                               _f64, _vp]),
     "noa_dcs_fp64_probe": (ctypes.c_int, [_i64, _i32, _i32, _vp, _vp]),
     "noa_dcs_fp64_probe_mode": (ctypes.c_int, [_i32, _i64, _i32, _i32, _vp, _vp]),
     "noa_dcs_set_pair_mode": (ctypes.c_int, [ctypes.c_int]),

@@ -32,7 +32,10 @@ namespace noa_b200 {
 
 __device__ const glibm::Tables g_tables = {GLIBM_EXP_TABLE_INIT, GLIBM_LOG_TABLE_INIT};
 
-constexpr int kThreads = 256;
+#ifndef NOA_THREADS
+#define NOA_THREADS 256
+#endif
+constexpr int kThreads = NOA_THREADS;
 
 // Minimum resident CTAs per SM requested from ptxas (register cap = 65536 / (256 * N)).
 // The kernels are bound by issue slots and fixed-latency dependencies, not by the FP64 pipe alone
@@ -72,6 +75,10 @@ __device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
     return glibm::make_smem_tab(dst);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ------------------------------------------------------------------------------------------
 // element-wise, one process
 // ------------------------------------------------------------------------------------------
@@ -83,12 +90,19 @@ vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *
     const glibm::Tab T = stage_tables(s_tables);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    // The next iteration's operands are requested (into L2) before the current pair is evaluated
+    // (free for device-resident arrays; K, q and out may also be pinned HOST buffers read and
+    // written in place over PCIe, noa_dcs_vmap_pinned_f64).
     if (VEC == 2) {
         const int64_t n2 = n >> 1;
         const double2 *K2 = reinterpret_cast<const double2 *>(K);
         const double2 *q2 = reinterpret_cast<const double2 *>(q);
         double2 *o2 = reinterpret_cast<double2 *>(out);
         for (int64_t i = tid; i < n2; i += stride) {
+            if (i + stride < n2) {
+                prefetch_l2(K2 + i + stride);
+                prefetch_l2(q2 + i + stride);
+            }
             const double2 k = K2[i];
             const double2 r = q2[i];
             double2 o;
@@ -98,7 +112,13 @@ vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *
         }
         if (tid == 0 && (n & 1)) out[n - 1] = dcs_eval<PROCESS>(K[n - 1], q[n - 1], p, T);
     } else {
-        for (int64_t i = tid; i < n; i += stride) out[i] = dcs_eval<PROCESS>(K[i], q[i], p, T);
+        for (int64_t i = tid; i < n; i += stride) {
+            if (i + stride < n) {
+                prefetch_l2(K + i + stride);
+                prefetch_l2(q + i + stride);
+            }
+            out[i] = dcs_eval<PROCESS>(K[i], q[i], p, T);
+        }
     }
 }
 
@@ -362,6 +382,23 @@ table_exchange_kernel(const double *__restrict__ K, int64_t nK, const __grid_con
     table_exchange_tail(out);
 }
 
+// Material tables: out[c] = sum_e parts[e][c] * w[e], e in composition order, starting from 0
+// (the per-element mixing of src/noa/3rdparty/_pumas/pumas.c:8054-8078).  `columns` = 8 n_K.
+struct MixWeights {
+    int32_t n_elements;
+    double w[NOA_DCS_MAX_ELEMENTS];
+};
+
+__global__ void mix_tables_kernel(const double *__restrict__ parts, double *__restrict__ out,
+                                  int64_t columns, const __grid_constant__ MixWeights m) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < columns; c += stride) {
+        double acc = 0.;
+        for (int e = 0; e < m.n_elements; e++) acc += parts[(int64_t) e * columns + c] * m.w[e];
+        out[c] = acc;
+    }
+}
+
 // A rank with no rows of its own still has to take part in the exchange.
 __global__ void table_signal_kernel(const __grid_constant__ TableOut out) {
     table_exchange_tail(out);
@@ -400,6 +437,112 @@ __global__ void fp64_probe_kernel(int64_t iters, double *sink) {
 #pragma unroll
     for (int j = 0; j < 16; j++) s += a[j];
     if (s == 123456.789) sink[0] = s;   // never true; keeps the chains alive
+}
+
+// Latency probe: CHAINS independent dependent-DFMA chains per thread (mode 0 is CHAINS = 16).
+template <int CHAINS>
+__global__ void fp64_chain_probe_kernel(int64_t iters, double *sink) {
+    double a[CHAINS];
+#pragma unroll
+    for (int j = 0; j < CHAINS; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+    const double kb = 0.999999, kc = 1e-6;
+    for (int64_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 16 / CHAINS; r++)
+#pragma unroll
+            for (int j = 0; j < CHAINS; j++) a[j] = fma(a[j], kb, kc);
+    }
+    double s = 0.;
+#pragma unroll
+    for (int j = 0; j < CHAINS; j++) s += a[j];
+    if (s == 123456.789) sink[0] = s;
+}
+
+// Constant-load probe: dependent DFMA chains (CHAINS per thread) whose multiplier is re-read from
+// the constant bank before every DFMA (ld.const through the LDC / IDC path, as the polynomial
+// coefficients of glibm are), to see what a constant load in the dependency chain costs.
+__constant__ double c_probe_consts[64] = {0.999999, 0.999998, 0.999997, 0.999996};
+template <int CHAINS, int UNIFORM>
+__global__ void fp64_ldc_probe_kernel(int64_t iters, double *sink) {
+    double a[CHAINS];
+#pragma unroll
+    for (int j = 0; j < CHAINS; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+    const double kc = 1e-6;
+    // UNIFORM = 1: the index follows the loop counter (LDCU, uniform datapath);
+    // UNIFORM = 0: it comes from the chain's own value, like a table lookup (LDC with a per-thread
+    // address)
+    for (int64_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 16 / CHAINS; r++)
+#pragma unroll
+            for (int j = 0; j < CHAINS; j++) {
+                const uint32_t idx = UNIFORM ? (uint32_t) (it + j + r)
+                                             : (uint32_t) __double2loint(a[j]);
+                const double kb = c_probe_consts[idx & 3u];
+                a[j] = fma(a[j], kb, kc);
+            }
+    }
+    double s = 0.;
+#pragma unroll
+    for (int j = 0; j < CHAINS; j++) s += a[j];
+    if (s == 123456.789) sink[0] = s;
+}
+
+// Same with the multiplier read from shared memory (LDS, warp-uniform address = broadcast).
+template <int CHAINS>
+__global__ void fp64_lds_probe_kernel(int64_t iters, double *sink) {
+    __shared__ double s_consts[64];
+    if (threadIdx.x < 64) s_consts[threadIdx.x] = 0.999999 - 1e-6 * (threadIdx.x & 3);
+    __syncthreads();
+    double a[CHAINS];
+#pragma unroll
+    for (int j = 0; j < CHAINS; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+    const double kc = 1e-6;
+    for (int64_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 16 / CHAINS; r++)
+#pragma unroll
+            for (int j = 0; j < CHAINS; j++) {
+                const double kb = s_consts[(uint32_t) (it + j + r) & 3u];
+                a[j] = fma(a[j], kb, kc);
+            }
+    }
+    double s = 0.;
+#pragma unroll
+    for (int j = 0; j < CHAINS; j++) s += a[j];
+    if (s == 123456.789) sink[0] = s;
+}
+
+// Issue-slot probe: 16 independent DFMA chains interleaved with NINT independent 32-bit integer
+// multiply-adds per DFMA.  If the time per DFMA does not grow with NINT <= 1, non-FP64 instructions
+// issue in the shadow of the half-rate FP64 dispatch; if it grows, they compete for issue cycles.
+template <int NINT>
+__global__ void fp64_mix_probe_kernel(int64_t iters, double *sink) {
+    double a[16];
+    uint32_t x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+        x[j] = threadIdx.x * 2654435761u + j;
+    }
+    const double kb = 0.999999, kc = 1e-6;
+    for (int64_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            a[j] = fma(a[j], kb, kc);
+#pragma unroll
+            for (int t = 0; t < NINT; t++)
+                asm volatile("mad.lo.u32 %0, %0, 1664525, 1013904223;" : "+r"(x[j]));
+        }
+    }
+    double s = 0.;
+    uint32_t y = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        s += a[j];
+        y ^= x[j];
+    }
+    if (s == 123456.789 || y == 0x12345678u) sink[0] = s + y;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -672,6 +815,35 @@ int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double
                       local_out(del, cel, nK), stream);
 }
 
+int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                               int32_t min_points, int32_t n_elements, const double *A,
+                               const double *I, const int32_t *Z, const double *w, double mass,
+                               double *scratch, double *table, void *stream) {
+    if (n_elements < 1 || n_elements > NOA_DCS_MAX_ELEMENTS || !A || !I || !Z || !w)
+        return NOA_DCS_EINVAL;
+    if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1) return NOA_DCS_EINVAL;
+    if (nK == 0) return 0;
+    if (!K || !scratch || !table) return NOA_DCS_EINVAL;
+    const int64_t columns = 8 * nK;
+    // rows of processes outside the mask must mix to 0, not to whatever the scratch held
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t) n_elements * columns * sizeof(double),
+                                    (cudaStream_t) stream);
+    if (e != cudaSuccess) return (int) e;
+    MixWeights m{};
+    m.n_elements = n_elements;
+    for (int el = 0; el < n_elements; el++) {
+        m.w[el] = w[el];
+        double *part = scratch + (int64_t) el * columns;
+        int rc = table_impl(process_mask, false, K, nK, xlow, min_points, A[el], I[el], Z[el], mass,
+                            local_out(part, part + 4 * nK, nK), stream);
+        if (rc) return rc;
+    }
+    const int64_t blocks = (columns + 255) / 256;
+    mix_tables_kernel<<<(unsigned) (blocks > 1184 ? 1184 : blocks), 256, 0,
+                        (cudaStream_t) stream>>>(scratch, table, columns, m);
+    return after_launch();
+}
+
 int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int64_t n_local,
                               double xlow, int32_t min_points, double A, double I, int32_t Z,
                               double mass, int32_t n_peers, double *const *peer_del,
@@ -826,6 +998,32 @@ int noa_dcs_vmap_host_f64(noa_dcs_stager *st, int process, const double *h_K, co
     return rc;
 }
 
+// 1 if `ptr` is page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)
+static bool device_addressable_host(const void *ptr) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        (void) cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+}
+
+int noa_dcs_vmap_pinned_f64(int process, const double *h_K, const double *h_q, double *h_result,
+                            int64_t n, double A, double I, int32_t Z, double mass, void *stream) {
+    if (process < 0 || process >= NOA_DCS_NPROCESS || n < 0) return NOA_DCS_EINVAL;
+    if (n == 0) return 0;
+    if (!h_K || !h_q || !h_result) return NOA_DCS_EINVAL;
+    if (!device_addressable_host(h_K) || !device_addressable_host(h_q) ||
+        !device_addressable_host(h_result))
+        return NOA_DCS_EINVAL;
+    // The element-wise kernels run unchanged on the mapped host addresses: their coalesced loads
+    // and stores cross PCIe themselves and overlap with the arithmetic of the other resident
+    // warps.  Measured alternatives (TMA bulk-copy ring with mbarriers; per-thread cp.async
+    // prefetch into shared memory) were slower or equal -- profiles/r01_host_path_variants.md.
+    const Params p = make_params(A, I, Z, mass);
+    return vmap_impl(process, h_K, h_q, h_result, n, p, (cudaStream_t) stream);
+}
+
 int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink,
                        void *stream) {
     if (iters < 1 || blocks < 1 || threads < 1 || threads > 1024 || !sink) return NOA_DCS_EINVAL;
@@ -843,6 +1041,19 @@ int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t
         case 2: fp64_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
         case 3: fp64_probe_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); break;
         case 4: fp64_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 5: fp64_mix_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 6: fp64_mix_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 7: fp64_mix_probe_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 20: fp64_ldc_probe_kernel<1, 1><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 21: fp64_ldc_probe_kernel<1, 0><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 22: fp64_ldc_probe_kernel<4, 1><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 23: fp64_ldc_probe_kernel<4, 0><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 24: fp64_lds_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 25: fp64_lds_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 10: fp64_chain_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 11: fp64_chain_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 12: fp64_chain_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
+        case 13: fp64_chain_probe_kernel<8><<<blocks, threads, 0, s>>>(iters, sink); break;
         default: return NOA_DCS_EINVAL;
     }
     return after_launch();

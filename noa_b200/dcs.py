@@ -376,16 +376,51 @@ class _Cuda:
         return del_t, cel_t
 
 
+    # -- material tables: element tables mixed by mass fraction (pumas.c:8054-8078)
+    @staticmethod
+    def material_tables(kinetic_energies, xlow, material, mass, min_points, processes=PROCESSES,
+                        scratch=None):
+        """Returns ([2, 4, n_K] material table, [n_elements, 2, 4, n_K] element tables)."""
+        lib = _lib.require_device()
+        _check_tensor(kinetic_energies, "kinetic_energies")
+        n = kinetic_energies.numel()
+        ne = len(material.elements)
+        mask = 0
+        for pr in processes:
+            mask |= 1 << pr.index
+        dev = kinetic_energies.device
+        if scratch is None:
+            scratch = torch.empty((ne, 2, 4, n), dtype=torch.float64, device=dev)
+        else:
+            _check_tensor(scratch, "scratch")
+            if scratch.numel() != ne * 8 * n:
+                raise ValueError(f"scratch must hold {ne} x 8 x {n} elements")
+        table = torch.zeros((2, 4, n), dtype=torch.float64, device=dev)
+        A = (ctypes.c_double * ne)(*[float(e.A) for e in material.elements])
+        I = (ctypes.c_double * ne)(*[float(e.I) for e in material.elements])
+        Z = (ctypes.c_int32 * ne)(*[int(e.Z) for e in material.elements])
+        w = (ctypes.c_double * ne)(*[float(f) for f in material.fractions])
+        if n:
+            with torch.cuda.device(dev):
+                _lib.check(lib.noa_dcs_table_material_f64(
+                    mask, _ptr(kinetic_energies), n, float(xlow), int(min_points), ne, A, I, Z, w,
+                    float(mass), _ptr(scratch), _ptr(table), _stream(dev)))
+        return table, scratch.view(ne, 2, 4, n)
+
+
 cuda = _Cuda()
 
 
 # ---- host-buffer path (the CPU-tensor drop-in: dcs::map(f) on CPU tensors) ------------------------
 class HostStager:
-    """Owns the device scratch + streams used to run CPU (ideally pinned) tensors through the GPU
-    with copies overlapped with compute (C ABI: noa_dcs_vmap_host_f64)."""
+    """Runs CPU tensors through the GPU.  Pinned tensors (one process): a single kernel reads and
+    writes the host arrays in place over PCIe (C ABI: noa_dcs_vmap_pinned_f64).  Pageable tensors,
+    or all four processes at once: chunked H2D / kernel / D2H pipeline over the stager's device
+    scratch and streams (C ABI: noa_dcs_vmap_host_f64).  Both block until `out` is complete."""
 
-    def __init__(self, chunk_pairs=1 << 20, n_slots=3, device=None):
+    def __init__(self, chunk_pairs=1 << 18, n_slots=3, device=None, zero_copy=True):
         self._lib = _lib.require_device()
+        self.zero_copy = zero_copy
         self._handle = ctypes.c_void_p()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
@@ -419,6 +454,16 @@ class HostStager:
             out = torch.empty(shape, dtype=torch.float64,
                               pin_memory=kinetic_energies.is_pinned())
         A, I, Z = _element(element)
+        if (dcs_func is not None and self.zero_copy and kinetic_energies.is_pinned()
+                and recoil_energies.is_pinned() and out.is_pinned() and out.is_contiguous()):
+            # page-locked buffers: the kernel reads and writes them in place over PCIe, no copies
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device)
+                _lib.check(self._lib.noa_dcs_vmap_pinned_f64(
+                    index, _ptr(kinetic_energies), _ptr(recoil_energies), _ptr(out), n, A, I, Z,
+                    float(mass), ctypes.c_void_p(stream.cuda_stream)))
+                stream.synchronize()
+            return out
         with torch.cuda.device(self.device):
             _lib.check(self._lib.noa_dcs_vmap_host_f64(self._handle, index, _ptr(kinetic_energies),
                                                       _ptr(recoil_energies), _ptr(out), n, A, I, Z,

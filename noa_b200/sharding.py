@@ -14,6 +14,33 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
+    buffers of the host-buffer path are allocated (first touch) in the memory next to the GPU's
+    PCIe root and the ranks of one box do not all pull from one socket.  Returns the node id, or
+    None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_range(n, rank, world):
     """Contiguous [lo, hi) of `n` items for `rank` of `world` (sizes differ by at most one)."""
     base, extra = divmod(n, world)

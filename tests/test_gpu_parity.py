@@ -169,6 +169,27 @@ def test_fused_tables_equal_single_columns(golden):
     assert torch.equal(d2[0], del_t[0]) and float(d2[1:].abs().sum()) == 0.0
 
 
+def test_material_tables_mix_element_tables(port):
+    """Water = H + O: table = sum_e t_e * w_e in composition order (pumas.c:8054-8078), with the
+    element tables themselves bit-identical to the oracle's recoil integrals."""
+    from noa_b200 import WATER
+    K = grids.table_energies(97, -2.0, 6.0)
+    table, parts = dcs.cuda.material_tables(dev(K), 0.05, WATER, MUON_MASS, 180)
+    assert table.shape == (2, 4, 97) and parts.shape == (2, 2, 4, 97)
+    want = np.zeros((2, 4, 97))
+    for e, (el, w) in enumerate(zip(WATER.elements, WATER.fractions)):
+        for ig in range(2):
+            for p in range(4):
+                t = port.vmap_integral(p, ig, K, 0.05, 180, tuple(el), MUON_MASS, threads=8)
+                assert_parity(parts[e, ig, p], t, ("element table", e, ig, p))
+                want[ig, p] += t * w
+    assert np.array_equal(table.cpu().numpy(), want)
+    # a process subset leaves the other rows at exactly zero
+    t2, _ = dcs.cuda.material_tables(dev(K), 0.05, WATER, MUON_MASS, 180,
+                                     processes=(dcs.photonuclear,))
+    assert torch.equal(t2[:, 2], table[:, 2]) and float(t2[:, [0, 1, 3]].abs().sum()) == 0.0
+
+
 def test_table_odd_node_counts(port):
     """min_points not a multiple of 6 and larger than one shared-memory pass (1536 nodes)."""
     K = grids.table_energies(24, -1.0, 5.0)
@@ -217,10 +238,20 @@ def test_host_stager_roundtrip(port):
     st = dcs.HostStager(chunk_pairs=1 << 16, n_slots=3)
     try:
         for pr in (dcs.bremsstrahlung, dcs.pair_production):
+            want = port.vmap(pr.index, K, q, ELEMENTS["rock"], MUON_MASS, threads=8)
+            out = st.map(pr, Kh, qh, ELEMENTS["rock"], MUON_MASS)      # pinned: in-place kernel
+            assert not out.is_cuda and out.is_pinned()
+            assert_parity(out, want, ("host pinned", pr.name))
+            # pageable tensors and an unaligned pinned view go through the copy pipeline / the
+            # scalar-load kernel
+            out = st.map(pr, torch.from_numpy(K), torch.from_numpy(q), ELEMENTS["rock"], MUON_MASS)
+            assert_parity(out, want, ("host pageable", pr.name))
+            out = st.map(pr, Kh[1:], qh[1:], ELEMENTS["rock"], MUON_MASS)
+            assert_parity(out, want[1:], ("host pinned, 8-byte aligned view", pr.name))
+            st.zero_copy = False
             out = st.map(pr, Kh, qh, ELEMENTS["rock"], MUON_MASS)
-            assert not out.is_cuda
-            assert_parity(out, port.vmap(pr.index, K, q, ELEMENTS["rock"], MUON_MASS, threads=8),
-                          ("host", pr.name))
+            st.zero_copy = True
+            assert_parity(out, want, ("host staged", pr.name))
         allp = st.map(None, Kh, qh, ELEMENTS["rock"], MUON_MASS)
         assert allp.shape == (4, 300001)
         assert_parity(allp[2], port.vmap(2, K, q, ELEMENTS["rock"], MUON_MASS, threads=8),

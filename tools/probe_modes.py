@@ -7,9 +7,10 @@ from noa_b200 import _lib
 lib = _lib.require_device()
 sink = torch.zeros(8, dtype=torch.float64, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-names = {0: "DFMA r*c+c (1 reg src)", 1: "DFMA r*r+r (3 reg src)", 2: "DFMA r*r+c (2 reg src)", 3: "DADD r+r", 4: "DMUL r*r"}
+names = {0: "DFMA r*c+c (1 reg src)", 1: "DFMA r*r+r (3 reg src)", 2: "DFMA r*r+c (2 reg src)", 3: "DADD r+r", 4: "DMUL r*r",
+         5: "DFMA + 1 IMAD", 6: "DFMA + 2 IMAD", 7: "DFMA + 3 IMAD"}
 out = {}
-for mode in range(5):
+for mode in range(8):
     best = 0
     for _ in range(4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
