@@ -244,6 +244,10 @@ int noa_dcs_set_pair_mode(int mode);
  * last one is for timing experiments: not a sufficient ordering). */
 int noa_dcs_set_exchange_fence_mode(int mode);
 
+/* Cap the resident CTAs per SM of the persistent element-wise kernels (0 = no cap; measurement hook
+ * for occupancy-scaling experiments). */
+int noa_dcs_set_max_blocks_per_sm(int blocks);
+
 /* Launch geometry the element-wise kernels use on the current device (for reporting). */
 int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t *sm_count);
 

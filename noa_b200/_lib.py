@@ -60,6 +60,7 @@ SIGNATURES = {
     "noa_dcs_fp64_probe_mode": (ctypes.c_int, [_i32, _i64, _i32, _i32, _vp, _vp]),
     "noa_dcs_set_pair_mode": (ctypes.c_int, [ctypes.c_int]),
     "noa_dcs_set_exchange_fence_mode": (ctypes.c_int, [ctypes.c_int]),
+    "noa_dcs_set_max_blocks_per_sm": (ctypes.c_int, [ctypes.c_int]),
     "noa_dcs_launch_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_i32),
                                            ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "noa_dcs_launch_count": (_i64, []),

@@ -578,6 +578,8 @@ static int device_info(DeviceInfo &info) {
     return 0;
 }
 
+static int g_max_blocks_per_sm = 0;   // measurement hook (0 = whatever fits)
+
 template <typename Kernel>
 static int persistent_grid(Kernel kernel, int64_t work_items, int &blocks) {
     DeviceInfo info;
@@ -587,6 +589,7 @@ static int persistent_grid(Kernel kernel, int64_t work_items, int &blocks) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (e != cudaSuccess) return (int) e;
     if (per_sm < 1) per_sm = 1;
+    if (g_max_blocks_per_sm > 0 && per_sm > g_max_blocks_per_sm) per_sm = g_max_blocks_per_sm;
     const int64_t need = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t) info.sm_count * per_sm;
     blocks = (int) (need < cap ? need : cap);
@@ -705,6 +708,12 @@ int64_t noa_dcs_launch_count(void) { return g_launches.load(); }
 int noa_dcs_set_pair_mode(int mode) {
     if (mode != 0 && mode != 1) return NOA_DCS_EINVAL;
     g_pair_mode = mode;
+    return 0;
+}
+
+int noa_dcs_set_max_blocks_per_sm(int blocks) {
+    if (blocks < 0) return NOA_DCS_EINVAL;
+    g_max_blocks_per_sm = blocks;
     return 0;
 }
 

@@ -62,3 +62,23 @@ def test_api_tokens_and_validation():
     bad = torch.ones(4, dtype=torch.float32)
     with pytest.raises((ValueError, Exception)):
         dcs.cuda.vmap_bremsstrahlung(bad, bad, bad, (22., 0.1364e-6, 11), 0.10565839)
+
+
+def test_libtorch_boundary_has_no_python_dependency_and_cli_refuses_cpu():
+    """libnoa_dcs_b200_torch.so is what a C++ user links: it must not need libpython.  The
+    benchmark executable built on it (benchmark/measure_dcs_calc_cuda.cc) must fail loudly without
+    a GPU instead of falling back to anything."""
+    import subprocess
+    import torch
+    so = os.path.join(ROOT, "noa_b200", "libnoa_dcs_b200_torch.so")
+    exe = os.path.join(ROOT, "noa_b200", "measure_dcs_calc_cuda")
+    if not (os.path.exists(so) and os.path.exists(exe)):
+        pytest.skip("LibTorch boundary not built here (python noa_b200/csrc/build_torch_ext.py)")
+    syms = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    assert " U Py" not in syms and "_Py_" not in syms
+    for name in ("vmap_bremsstrahlung", "map_bremsstrahlung", "vmap_integral", "tables",
+                 "coulomb_data", "coulomb_transport", "hard_scattering", "soft_scattering"):
+        assert name in syms, name
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU path" in r.stderr

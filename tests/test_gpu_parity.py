@@ -293,3 +293,24 @@ def test_cpp_libtorch_boundary_via_pybind(golden):
         muons.bremsstrahlung(K.float(), q.float())
     with pytest.raises(RuntimeError):
         muons.bremsstrahlung(K.cpu(), q.cpu())
+
+
+def test_reference_benchmark_cases_cli():
+    """benchmark/measure_dcs_calc_cuda: every case name of the reference's measure-dcs-calc harness
+    that has a GPU form prints one Google-Benchmark-style line."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "noa_b200", "measure_dcs_calc_cuda")
+    if not os.path.exists(exe):
+        pytest.skip("benchmark executable not built")
+    r = subprocess.run([exe, "--benchmark_min_time=0.02"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    for case in ("BremsstrahlungVectorisedCUDA", "BremsstrahlungVectorisedLargeCUDA",
+                 "PairProductionVectorisedCUDA", "PhotonuclearVectorisedLargeCUDA",
+                 "DELIonisationVectorisedCUDA", "CELPairProductionVectorisedCUDA",
+                 "CoulombHardScatteringCUDA", "CoulombSoftScatteringCUDA"):
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("DCSBenchmark/" + case + " ")]
+        assert len(lines) == 1, case
+        assert float(lines[0].split()[1]) > 0
