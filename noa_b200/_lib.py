@@ -64,6 +64,7 @@ SIGNATURES = {
     "noa_dcs_launch_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_i32),
                                            ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "noa_dcs_launch_count": (_i64, []),
+    "noa_dcs_div_recomputes": (ctypes.c_int, [ctypes.POINTER(_i64), ctypes.c_int]),
 }
 
 

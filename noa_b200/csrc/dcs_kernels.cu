@@ -47,7 +47,7 @@ constexpr int kThreads = NOA_THREADS;
 #define NOA_MINB_PAIR 4
 #endif
 #ifndef NOA_MINB_PHOTO
-#define NOA_MINB_PHOTO 4
+#define NOA_MINB_PHOTO 3
 #endif
 #ifndef NOA_MINB_STREAM
 #define NOA_MINB_STREAM 5
@@ -75,6 +75,63 @@ __device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
     return glibm::make_smem_tab(dst);
 }
 
+// Evaluation of one DCS value with the folded division checks of fdiv.cuh: the FastDiv pass, and
+// -- only if one of its divisions left nvcc's fast-path domain (zero / subnormal-range numerator,
+// non-finite or out-of-range quotient) -- the same value again with plain IEEE division, out of
+// line.  g_div_recomputes counts those second passes (diagnostics: noa_dcs_div_recomputes).
+#ifndef NOA_FAST_DIV
+#define NOA_FAST_DIV 1
+#endif
+__device__ unsigned long long g_div_recomputes = 0;
+
+// Tables plus the refined reciprocals of the launch-invariant denominators (fdiv.cuh: DenSlot).
+struct StagedShared {
+    glibm::Tables tables;
+    double dens[kDenSlots];
+};
+
+__device__ __forceinline__ glibm::Tab stage_all(StagedShared &dst, const Params &p) {
+    if (threadIdx.x < kDenSlots) {
+        double b;
+        switch (threadIdx.x) {
+            case kDenLambda2: b = 0.06527; break;
+            case kDenQ004: b = 0.04; break;
+            case kDenLogQ0L: b = p.n_logq0l; break;
+            case kDenR2: b = p.p_r2; break;
+            case kDenA: b = p.A; break;
+            case kDenMass: b = p.mass; break;
+            case kDenMe: b = kElectronMass; break;
+            default: b = p.i_m2; break;
+        }
+        dst.dens[threadIdx.x] = FastDivT<true>::staged_reciprocal(b);
+    }
+    glibm::Tab T = stage_tables(dst.tables);
+    T.aux_smem = T.exp_smem + (uint32_t) offsetof(StagedShared, dens);
+    return T;
+}
+
+template <int PROCESS>
+__device__ __noinline__ double dcs_eval_ieee(double K, double q, const Params &p,
+                                             const glibm::Tab &T) {
+    atomicAdd(&g_div_recomputes, 1ULL);
+    return dcs_eval<PROCESS>(K, q, p, T);
+}
+
+// STAGED = T comes from stage_all() for this very `p`
+template <int PROCESS, bool STAGED>
+__device__ __forceinline__ double dcs_value(double K, double q, const Params &p,
+                                            const glibm::Tab &T) {
+#if NOA_FAST_DIV
+    FastDivT<STAGED> dv;
+    dv.dens = T.aux_smem;
+    double v = dcs_eval<PROCESS>(K, q, p, T, dv);
+    if (!dv.ok()) v = dcs_eval_ieee<PROCESS>(K, q, p, T);
+    return v;
+#else
+    return dcs_eval<PROCESS>(K, q, p, T);
+#endif
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -86,8 +143,8 @@ template <int PROCESS, int VEC>
 __global__ void __launch_bounds__(kThreads, MinBlocks<PROCESS>::value)
 vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *__restrict__ out,
             int64_t n, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables s_tables;
-    const glibm::Tab T = stage_tables(s_tables);
+    __shared__ StagedShared s_staged;
+    const glibm::Tab T = stage_all(s_staged, p);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     // The next iteration's operands are requested (into L2) before the current pair is evaluated
@@ -106,18 +163,18 @@ vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *
             const double2 k = K2[i];
             const double2 r = q2[i];
             double2 o;
-            o.x = dcs_eval<PROCESS>(k.x, r.x, p, T);
-            o.y = dcs_eval<PROCESS>(k.y, r.y, p, T);
+            o.x = dcs_value<PROCESS, true>(k.x, r.x, p, T);
+            o.y = dcs_value<PROCESS, true>(k.y, r.y, p, T);
             o2[i] = o;
         }
-        if (tid == 0 && (n & 1)) out[n - 1] = dcs_eval<PROCESS>(K[n - 1], q[n - 1], p, T);
+        if (tid == 0 && (n & 1)) out[n - 1] = dcs_value<PROCESS, true>(K[n - 1], q[n - 1], p, T);
     } else {
         for (int64_t i = tid; i < n; i += stride) {
             if (i + stride < n) {
                 prefetch_l2(K + i + stride);
                 prefetch_l2(q + i + stride);
             }
-            out[i] = dcs_eval<PROCESS>(K[i], q[i], p, T);
+            out[i] = dcs_value<PROCESS, true>(K[i], q[i], p, T);
         }
     }
 }
@@ -154,15 +211,15 @@ vmap_pair_lanes_kernel(const double *__restrict__ K, const double *__restrict__ 
 __global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
 vmap_all_kernel(const double *__restrict__ K, const double *__restrict__ q,
                 double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables s_tables;
-    const glibm::Tab T = stage_tables(s_tables);
+    __shared__ StagedShared s_staged;
+    const glibm::Tab T = stage_all(s_staged, p);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double k = K[i], r = q[i];
-        out[i] = bremsstrahlung(k, r, p, T);
-        out[n + i] = pair_production(k, r, p, T);
-        out[2 * n + i] = photonuclear(k, r, p, T);
-        out[3 * n + i] = ionisation(k, r, p, T);
+        out[i] = dcs_value<0, true>(k, r, p, T);
+        out[n + i] = dcs_value<1, true>(k, r, p, T);
+        out[2 * n + i] = dcs_value<2, true>(k, r, p, T);
+        out[3 * n + i] = dcs_value<3, true>(k, r, p, T);
     }
 }
 
@@ -173,13 +230,14 @@ struct Mixture {
     Params p[NOA_DCS_MAX_ELEMENTS];
 };
 
+template <bool STAGED>
 __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, const Params &p,
                                                const glibm::Tab &T) {
     switch (process) {
-        case 0: return bremsstrahlung(k, r, p, T);
-        case 1: return pair_production(k, r, p, T);
-        case 2: return photonuclear(k, r, p, T);
-        default: return ionisation(k, r, p, T);
+        case 0: return dcs_value<0, STAGED>(k, r, p, T);
+        case 1: return dcs_value<1, STAGED>(k, r, p, T);
+        case 2: return dcs_value<2, STAGED>(k, r, p, T);
+        default: return dcs_value<3, STAGED>(k, r, p, T);
     }
 }
 
@@ -198,7 +256,7 @@ vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
             double acc = 0.;
 #pragma unroll 1
             for (int e = 0; e < m.n_elements; e++)
-                acc += m.w[e] * dcs_dispatch(process, k, r, m.p[e], T);
+                acc += m.w[e] * dcs_dispatch<false>(process, k, r, m.p[e], T);
             out[(int64_t) slot * n + i] = acc;
             slot++;
         }
@@ -320,7 +378,7 @@ __device__ NOA_TABLE_ROW_INLINE void table_row(int64_t b, const double *__restri
             const uint32_t j = i % 6u;
             const double x = lb + h * ((i / 6u) + c_gl6_x[j]);
             const double r = glibm::exp(x, T);
-            const double f = dcs_dispatch(process, k, r, p, T);
+            const double f = dcs_dispatch<true>(process, k, r, p, T);
             const double w = c_gl6_w[j];
             const double fr = f * r;
             s_del[i - base] = fr * h * w;           // del_integrand, dcs.hh:107-109
@@ -348,10 +406,10 @@ __device__ NOA_TABLE_ROW_INLINE void table_row(int64_t b, const double *__restri
 __global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
 table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
              const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables s_tables;
+    __shared__ StagedShared s_staged;
     __shared__ double s_del[kTableChunk];
     __shared__ double s_cel[kTableChunk];
-    const glibm::Tab T = stage_tables(s_tables);
+    const glibm::Tab T = stage_all(s_staged, p);
     table_row(blockIdx.x, K, nK, out, plan, p, T, s_del, s_cel);
     // the writer lanes fence their own remote stores (fence_mode 0)
     if (out.n_peers > 1 && out.fence_mode == 0 && (threadIdx.x == 0 || threadIdx.x == 32))
@@ -366,11 +424,11 @@ table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ T
 __global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
 table_exchange_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
                       const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables s_tables;
+    __shared__ StagedShared s_staged;
     __shared__ double s_del[kTableChunk];
     __shared__ double s_cel[kTableChunk];
     __shared__ uint32_t s_item[2];
-    const glibm::Tab T = stage_tables(s_tables);
+    const glibm::Tab T = stage_all(s_staged, p);
     const uint32_t total = (uint32_t) (nK * plan.n_slots);
     if (threadIdx.x == 64) s_item[0] = atomicAdd(out.done + 2, 1u);
     for (int cur = 0;; cur ^= 1) {
@@ -703,6 +761,19 @@ int noa_dcs_device_count(void) {
 }
 
 int64_t noa_dcs_launch_count(void) { return g_launches.load(); }
+
+int noa_dcs_div_recomputes(int64_t *count, int reset) {
+    unsigned long long v = 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(&v, g_div_recomputes, sizeof(v));
+    if (e == cudaSuccess && reset) {
+        const unsigned long long zero = 0;
+        e = cudaMemcpyToSymbol(g_div_recomputes, &zero, sizeof(zero));
+    }
+    if (e != cudaSuccess) return (int) e;
+    if (count) *count = (int64_t) v;
+    return 0;
+}
 
 // test/bench hook: 0 = pair per thread, 1 = node per lane.  Not part of the reference surface.
 int noa_dcs_set_pair_mode(int mode) {

@@ -6,7 +6,9 @@
 //   * sub-expressions that depend only on (element, projectile mass) are evaluated once on the
 //     host (dcs_params.hh) with the same operand order and handed over in `Params`;
 //   * exp/log/log10 are glibm:: (glibm.cuh), the table-driven routines glibc itself runs.
-// Division and sqrt are CUDA's IEEE-correct ones.  The translation unit is compiled with
+// Division goes through a policy object (fdiv.cuh): IeeeDiv is the plain `/`; FastDiv (device
+// only) is the same correctly-rounded quotient with the range checks of all divisions of one DCS
+// value folded into one flag.  sqrt is CUDA's IEEE-correct one.  The translation unit is compiled with
 // -fmad=false so that no multiply-add is contracted; the reference's benchmark/test builds
 // (-O3, x86-64 baseline) contain no FMA either.
 //
@@ -16,6 +18,7 @@
 #pragma once
 
 #include "glibm.cuh"
+#include "fdiv.cuh"
 
 namespace noa_b200 {
 
@@ -87,24 +90,27 @@ static const double h_gl9_w[9] = NOA_GL9_W;
 // ------------------------------------------------------------------------------------------
 // Bremsstrahlung -- src/noa/pms/physics.hh:114-153
 // ------------------------------------------------------------------------------------------
-NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tab &T) {
+template <class DV>
+NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
     const double me = kElectronMass;
     const double sqrte = 1.648721271;
     const double E = K + p.mass;
-    const double delta_factor = p.b_hm2 / E;
-    const double qe_max = E / (1. + p.b_hm2 / (me * E));
-    const double nu = q / E;
-    const double delta = delta_factor * nu / (1. - nu);
-    double phi_n = glibm::log(p.b_bzn * (p.mass + delta * p.b_c1) /
-                                  (p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
+    const typename DV::Den by_E = dv.den(E);
+    const double delta_factor = dv.div(p.b_hm2, by_E);
+    const double qe_max = dv.div(E, 1. + dv.div(p.b_hm2, me * E));
+    const double nu = dv.div(q, by_E);
+    const double delta = dv.div(delta_factor * nu, 1. - nu);
+    double phi_n = glibm::log(dv.div(p.b_bzn * (p.mass + delta * p.b_c1),
+                                     p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
     if (phi_n < 0.) phi_n = 0.;
     double phi_e = 0.;
     if (q < qe_max) {
-        phi_e = glibm::log(p.b_bzem / ((1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
+        phi_e = glibm::log(dv.div(p.b_bzem,
+                                  (1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
         if (phi_e < 0.) phi_e = 0.;
     }
-    const double s = p.b_pref * (p.Zd * phi_n + phi_e) * (4. / 3. * (1. / nu - 1.) + nu);
-    return (s < 0.) ? 0. : s * 1E+03 * kAvogadro / p.A;
+    const double s = p.b_pref * (p.Zd * phi_n + phi_e) * (4. / 3. * (dv.rcp(nu) - 1.) + nu);
+    return (s < 0.) ? 0. : dv.div_slot(s * 1E+03 * kAvogadro, p.A, kDenA);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -115,45 +121,48 @@ struct PairKinematics {   // per-(K,q) quantities of src/noa/pms/dcs.hh:159-176
 };
 
 // Kinematic window and integration bound; false = the DCS is exactly 0 (dcs.hh:151-156,174-175)
+template <class DV>
 NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tab &T,
-                       PairKinematics &k) {
+                       PairKinematics &k, DV &dv) {
     if (q <= 4. * kElectronMass) return false;
     if (q >= K + p.p_thr) return false;
-    const double nu = q / (K + p.mass);
-    k.beta = 0.5 * nu * nu / (1. - nu);
+    const double nu = dv.div(q, K + p.mass);
+    k.beta = dv.div(0.5 * nu * nu, 1. - nu);
     k.xi_factor = p.p_hr2 * k.beta;
-    k.gamma = 1. + K / p.mass;
-    const double x0 = 4. * kElectronMass / q;
-    const double x1 = 6. / (k.gamma * (k.gamma - q / p.mass));
-    const double argmin = (x0 + 2. * (1. - x0) * x1) / (1. + (1. - x1) * sqrt(1. - x0));
+    k.gamma = 1. + dv.div_slot(K, p.mass, kDenMass);
+    const double x0 = dv.div(4. * kElectronMass, q);
+    const double x1 = dv.div(6., k.gamma * (k.gamma - dv.div_slot(q, p.mass, kDenMass)));
+    const double argmin = dv.div(x0 + 2. * (1. - x0) * x1, 1. + (1. - x1) * sqrt(1. - x0));
     if ((argmin >= 1.) || (argmin <= 0.)) return false;
     k.tmin = glibm::log(argmin, T);
     return true;
 }
 
 // Integrand of the t = ln(1-rho) integral at node t (dcs.hh:179-227)
+template <class DV>
 NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Params &p,
-                        const glibm::Tab &T) {
+                        const glibm::Tab &T, DV &dv) {
     const double beta = k.beta;
     const double eps = glibm::exp(t * k.tmin, T);
     const double rho = 1. - eps;
     const double rho2 = rho * rho;
     const double rho21 = eps * (2. - eps);
     const double xi = k.xi_factor * rho21;
-    const double xi_i = 1. / xi;
+    const double xi_i = dv.rcp(xi);
+    const typename DV::Den by_1xi = dv.den(1. + xi);     // shared by Be and Bmu
 
     double Be;
     if (xi >= 1E+03)
         Be = 0.5 * xi_i * ((3 - rho2) + 2. * beta * (1. + rho2));
     else
         Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) * glibm::log(1. + xi_i, T) +
-             (rho21 - beta) / (1. + xi) - 3. - rho2;
-    const double Ye = (5. - rho2 + 4. * beta * (1. + rho2)) /
-                      (2. * (1. + 3. * beta) * glibm::log(3. + xi_i, T) - rho2 -
-                       2. * beta * (2. - rho2));
+             dv.div(rho21 - beta, by_1xi) - 3. - rho2;
+    const double Ye = dv.div(5. - rho2 + 4. * beta * (1. + rho2),
+                             2. * (1. + 3. * beta) * glibm::log(3. + xi_i, T) - rho2 -
+                                     2. * beta * (2. - rho2));
     const double xe = (1. + xi) * (1. + Ye);
-    const double cLi = p.p_cl / rho21;
-    const double Le = glibm::log(p.p_az13 * sqrt(xe) * q / (q + cLi * xe), T) -
+    const double cLi = dv.div(p.p_cl, rho21);
+    const double Le = glibm::log(dv.div(p.p_az13 * sqrt(xe) * q, q + cLi * xe), T) -
                       0.5 * glibm::log(1. + p.p_cle * xe, T);
     double phi_e = Be * Le;
     if (phi_e < 0.) phi_e = 0.;
@@ -163,53 +172,58 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
         Bmu = 0.5 * xi * (5. - rho2 + beta * (3. + rho2));
     else
         Bmu = ((1. + rho2) * (1. + 1.5 * beta) - xi_i * (1. + 2. * beta) * rho21) *
-                  glibm::log(1. + xi, T) +
-              xi * (rho21 - beta) / (1. + xi) + (1. + 2. * beta) * rho21;
-    const double Ymu = (4. + rho2 + 3. * beta * (1. + rho2)) /
-                       ((1. + rho2) * (1.5 + 2. * beta) * glibm::log(3. + xi, T) + 1. -
-                        1.5 * rho2);
+                      glibm::log(1. + xi, T) +
+              dv.div(xi * (rho21 - beta), by_1xi) + (1. + 2. * beta) * rho21;
+    const double Ymu = dv.div(4. + rho2 + 3. * beta * (1. + rho2),
+                              (1. + rho2) * (1.5 + 2. * beta) * glibm::log(3. + xi, T) + 1. -
+                                      1.5 * rho2);
     const double xmu = (1. + xi) * (1. + Ymu);
-    const double Lmu = glibm::log(p.p_raz13 * q / (p.p_z15 * (q + cLi * xmu)), T);
+    const double Lmu = glibm::log(dv.div(p.p_raz13 * q, p.p_z15 * (q + cLi * xmu)), T);
     double phi_mu = Bmu * Lmu;
     if (phi_mu < 0.) phi_mu = 0.;
-    return -(phi_e + phi_mu / p.p_r2) * (1. - rho) * k.tmin;
+    return -(phi_e + dv.div_slot(phi_mu, p.p_r2, kDenR2)) * (1. - rho) * k.tmin;
 }
 
 // Atomic-electron form factor and normalisation (dcs.hh:229-257); `integral` is the 8-node sum
+template <class DV>
 NOA_HD double pair_finish(double K, double q, double integral, const PairKinematics &k,
-                          const Params &p, const glibm::Tab &T) {
+                          const Params &p, const glibm::Tab &T, DV &dv) {
     const double gamma = k.gamma;
     double zeta;
     if (gamma <= 35.)
         zeta = 0.;
     else {
-        zeta = 0.073 * glibm::log(gamma / (1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
+        zeta = 0.073 * glibm::log(dv.div(gamma, 1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
                0.26;
         if (zeta <= 0.)
             zeta = 0.;
         else
-            zeta /= 0.058 * glibm::log(gamma / (1. + p.p_g2 * gamma * p.p_z13), T) - 0.14;
+            zeta = dv.div(zeta, 0.058 * glibm::log(dv.div(gamma, 1. + p.p_g2 * gamma * p.p_z13),
+                                                   T) - 0.14);
     }
     const double E = K + p.mass;
-    const double s = p.p_cz * (p.Zd + zeta) * (E - q) * integral / (q * E);
-    return (s < 0.) ? 0. : s * 1E+03 * kAvogadro * (p.mass + K) / p.A;
+    const double s = dv.div(p.p_cz * (p.Zd + zeta) * (E - q) * integral, q * E);
+    return (s < 0.) ? 0. : dv.div_slot(s * 1E+03 * kAvogadro * (p.mass + K), p.A, kDenA);
 }
 
 // One thread does all 8 nodes; accumulation order of numerics.hh:84-87 (h = 1, lb = 0)
-NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T) {
+template <class DV>
+NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
     PairKinematics k;
-    if (!pair_setup(K, q, p, T, k)) return 0.;
+    if (!pair_setup(K, q, p, T, k, dv)) return 0.;
     double acc = 0.;
     NOA_NODE_LOOP
-    for (int j = 0; j < 8; j++) acc += pair_node(NOA_GL(8, x, j), q, k, p, T) * NOA_GL(8, w, j);
-    return pair_finish(K, q, acc, k, p, T);
+    for (int j = 0; j < 8; j++)
+        acc += pair_node(NOA_GL(8, x, j), q, k, p, T, dv) * NOA_GL(8, w, j);
+    return pair_finish(K, q, acc, k, p, T, dv);
 }
 
 // ------------------------------------------------------------------------------------------
 // Photonuclear -- src/noa/pms/dcs.hh:261-405
 // ------------------------------------------------------------------------------------------
 // ALLM97 F2 (dcs.hh:261-307)
-NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T) {
+template <class DV>
+NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T, DV &dv) {
     const double m02 = 0.31985, mP2 = 49.457, mR2 = 0.15052, Q02 = 0.52544, Lambda2 = 0.06527;
     const double cP1 = 0.28067, cP2 = 0.22291, cP3 = 2.1979;
     const double aP1 = -0.0808, aP2 = -0.44812, aP3 = 1.1709;
@@ -219,13 +233,14 @@ NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T)
     const double bR1 = 0.01147, bR2 = 3.7582, bR3 = 0.49338;
     const double M2 = 0.8803505929;
 
-    const double W2 = M2 + Q2 * (1.0 / x - 1.0);
-    const double t = glibm::log(glibm::log((Q2 + Q02) / Lambda2, T) / p.n_logq0l, T);
-    const double xP = (Q2 + mP2) / (Q2 + mP2 + W2 - M2);
-    const double xR = (Q2 + mR2) / (Q2 + mR2 + W2 - M2);
+    const double W2 = M2 + Q2 * (dv.rcp(x) - 1.0);
+    const double t = glibm::log(dv.div_slot(glibm::log(dv.div_slot(Q2 + Q02, Lambda2, kDenLambda2), T),
+                                        p.n_logq0l, kDenLogQ0L), T);
+    const double xP = dv.div(Q2 + mP2, Q2 + mP2 + W2 - M2);
+    const double xR = dv.div(Q2 + mR2, Q2 + mR2 + W2 - M2);
     const double lnt = glibm::log(t, T);
-    const double cP = cP1 + (cP1 - cP2) * (1.0 / (1.0 + glibm::exp(cP3 * lnt, T)) - 1.0);
-    const double aP = aP1 + (aP1 - aP2) * (1.0 / (1.0 + glibm::exp(aP3 * lnt, T)) - 1.0);
+    const double cP = cP1 + (cP1 - cP2) * (dv.rcp(1.0 + glibm::exp(cP3 * lnt, T)) - 1.0);
+    const double aP = aP1 + (aP1 - aP2) * (dv.rcp(1.0 + glibm::exp(aP3 * lnt, T)) - 1.0);
     const double bP = bP1 + bP2 * glibm::exp(bP3 * lnt, T);
     const double cR = cR1 + cR2 * glibm::exp(cR3 * lnt, T);
     const double aR = aR1 + aR2 * glibm::exp(aR3 * lnt, T);
@@ -234,7 +249,7 @@ NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T)
     const double l1x = glibm::log(1 - x, T);
     const double F2P = cP * glibm::exp(aP * glibm::log(xP, T) + bP * l1x, T);
     const double F2R = cR * glibm::exp(aR * glibm::log(xR, T) + bR * l1x, T);
-    return Q2 / (Q2 + m02) * (F2P + F2R);
+    return dv.div(Q2, Q2 + m02) * (F2P + F2R);
 }
 
 // DRSS shadowing (dcs.hh:310-319)
@@ -248,89 +263,99 @@ NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tab &
 }
 
 // Whitlow R (dcs.hh:322-332)
-NOA_HD double r_whitlow(double x, double Q2, const glibm::Tab &T) {
+template <class DV>
+NOA_HD double r_whitlow(double x, double Q2, const glibm::Tab &T, DV &dv) {
     double q2 = Q2;
     if (Q2 < 0.3) q2 = 0.3;
-    const double theta = 1 + 12.0 * q2 / (1.0 + q2) * 0.015625 / (0.015625 + x * x);
-    return (0.635 / glibm::log(q2 / 0.04, T) * theta + 0.5747 / q2 -
-            0.3534 / (0.09 + q2 * q2));
+    const double theta = 1 + dv.div(dv.div(12.0 * q2, 1.0 + q2) * 0.015625, 0.015625 + x * x);
+    return (dv.div(0.635, glibm::log(dv.div_slot(q2, 0.04, kDenQ004), T)) * theta + dv.div(0.5747, q2) -
+            dv.div(0.3534, 0.09 + q2 * q2));
 }
 
+template <class DV>
 struct PhotoKinematics {   // per-(K,q) quantities of dcs.hh:372-387 and 340-342
-    double centre, width, E, y, Mq;
+    double centre, width, y;
+    typename DV::Den by_Mq, by_E2, by_q;   // denominators shared by the 9 nodes
 };
 
+template <class DV>
 NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm::Tab &T,
-                               PhotoKinematics &k) {
+                               PhotoKinematics<DV> &k, DV &dv) {
     if ((q < 1.) || (q < 2E-03 * K)) return false;            // dcs.hh:357-359
     const double M = 0.931494;
     const double mpi = 0.134977;
     const double E = K + p.mass;
     if ((q >= (E - p.mass)) || (q <= p.n_qpi)) return false;  // dcs.hh:374
-    const double y = q / E;
-    const double Q2min = p.n_m2 * y * y / (1 - y);
+    const double y = dv.div(q, E);
+    const double Q2min = dv.div(p.n_m2 * y * y, 1 - y);
     const double Q2max = 2.0 * M * (q - mpi) - mpi * mpi;
     if ((Q2max < Q2min) | (Q2min < 0)) return false;
     const double lo = glibm::log(Q2min, T);
     const double hi = glibm::log(Q2max, T);
     k.width = hi - lo;
     k.centre = 0.5 * (hi + lo);
-    k.E = E;
     k.y = y;
-    k.Mq = M * q;
+    k.by_Mq = dv.den(M * q);
+    k.by_E2 = dv.den(E * E);
+    k.by_q = dv.den(q);
     return true;
 }
 
 // d2sigma/dq dQ2 * Q2 at node t in [-1,1] (dcs.hh:335-355, 397-402)
-NOA_HD double photonuclear_node(double t, double q, const PhotoKinematics &k, const Params &p,
-                                const glibm::Tab &T) {
+template <class DV>
+NOA_HD double photonuclear_node(double t, const PhotoKinematics<DV> &k, const Params &p,
+                                const glibm::Tab &T, DV &dv) {
     const double cf = 2.603096E-35;
     const double Q2 = glibm::exp(k.centre + 0.5 * k.width * t, T);
-    const double E = k.E;
     const double y = k.y;
-    const double x = 0.5 * Q2 / k.Mq;
-    const double F2p = f2_allm(x, Q2, p, T);
+    const double x = dv.div(0.5 * Q2, k.by_Mq);
+    const double F2p = f2_allm(x, Q2, p, T, dv);
     const double F2A = f2a_drss(x, F2p, p, T);
-    const double R = r_whitlow(x, Q2, T);
+    const double R = r_whitlow(x, Q2, T, dv);
     const double dds =
-            (1 - y + 0.5 * (1 - p.n_2m2 / Q2) * (y * y + Q2 / (E * E)) / (1 + R)) / (Q2 * Q2) -
-            0.25 / (E * E * Q2);
-    return cf * F2A * dds / q * Q2;
+            dv.div(1 - y + dv.div(0.5 * (1 - dv.div(p.n_2m2, Q2)) * (y * y + dv.div(Q2, k.by_E2)),
+                                  1 + R),
+                   Q2 * Q2) -
+            dv.div(0.25, k.by_E2.b * Q2);
+    return dv.div(cf * F2A * dds, k.by_q) * Q2;
 }
 
-NOA_HD double photonuclear_finish(double K, double ds, const PhotoKinematics &k, const Params &p) {
-    return (ds < 0.) ? 0. : 0.5 * ds * k.width * 1E+03 * kAvogadro * (p.mass + K) / p.A;
-}
-
-NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab &T) {
-    PhotoKinematics k;
-    if (!photonuclear_setup(K, q, p, T, k)) return 0.;
+template <class DV>
+NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
+    PhotoKinematics<DV> k;
+    if (!photonuclear_setup(K, q, p, T, k, dv)) return 0.;
     double acc = 0.;
     NOA_NODE_LOOP
     for (int j = 0; j < 9; j++)
-        acc += photonuclear_node(NOA_GL(9, x, j), q, k, p, T) * NOA_GL(9, w, j);
-    return photonuclear_finish(K, acc, k, p);
+        acc += photonuclear_node(NOA_GL(9, x, j), k, p, T, dv) * NOA_GL(9, w, j);
+    return (acc < 0.) ? 0.
+                      : dv.div_slot(0.5 * acc * k.width * 1E+03 * kAvogadro * (p.mass + K), p.A,
+                                    kDenA);
 }
 
 // ------------------------------------------------------------------------------------------
 // Ionisation -- src/noa/pms/dcs.hh:408-443
 // ------------------------------------------------------------------------------------------
-NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &T) {
+template <class DV>
+NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
     const double me = kElectronMass;
     const double P2 = K * (K + 2. * p.mass);
     const double E = K + p.mass;
-    const double Wmax = 2. * me * P2 / (p.i_m2 + me * (me + 2. * E));
+    const double Wmax = dv.div(2. * me * P2, p.i_m2 + me * (me + 2. * E));
     if ((Wmax < kXFraction * K) || (q > Wmax)) return 0.;
     if (q <= p.i_wmin) return 0.;
-    const double a0 = 0.5 / P2;
-    const double a1 = -1. / Wmax;
-    const double a2 = E * E / P2;
-    const double cs = 1.535336E-05 * E * p.Zd / p.A * (a0 + 1. / q * (a1 + a2 / q));
+    const typename DV::Den by_P2 = dv.den(P2);
+    const double a0 = dv.div(0.5, by_P2);
+    const double a1 = dv.div(-1., Wmax);
+    const double a2 = dv.div(E * E, by_P2);
+    const typename DV::Den by_q = dv.den(q);
+    const double cs = dv.div_slot(1.535336E-05 * E * p.Zd, p.A, kDenA) *
+                      (a0 + dv.div(1., by_q) * (a1 + dv.div(a2, by_q)));
     double Delta = 0.;
     if (K >= p.i_kthr) {
-        const double L1 = glibm::log(1. + 2. * q / me, T);
+        const double L1 = glibm::log(1. + dv.div_slot(2. * q, me, kDenMe), T);
         Delta = 1.16141E-03 * L1 *
-                (glibm::log(4. * E * (E - q) / p.i_m2, T) - L1);
+                (glibm::log(dv.div_slot(4. * E * (E - q), p.i_m2, kDenIm2), T) - L1);
     }
     return cs * (1. + Delta);
 }
@@ -356,6 +381,47 @@ NOA_HD double ionisation_closed_form(double K, double xlow, int integrand, const
         term = 0.5 * a0 * (Wmax * Wmax - Wmin * Wmin) + a1 * (Wmax - Wmin) +
                a2 * glibm::log(Wmax / Wmin, T);
     return 1.535336E-05 * p.Zd / p.A * term;
+}
+
+// ---- plain-division forms (host build, table and Coulomb kernels, recompute path) -------------
+NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tab &T) {
+    IeeeDiv dv;
+    return bremsstrahlung(K, q, p, T, dv);
+}
+NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tab &T,
+                       PairKinematics &k) {
+    IeeeDiv dv;
+    return pair_setup(K, q, p, T, k, dv);
+}
+NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Params &p,
+                        const glibm::Tab &T) {
+    IeeeDiv dv;
+    return pair_node(t, q, k, p, T, dv);
+}
+NOA_HD double pair_finish(double K, double q, double integral, const PairKinematics &k,
+                          const Params &p, const glibm::Tab &T) {
+    IeeeDiv dv;
+    return pair_finish(K, q, integral, k, p, T, dv);
+}
+NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T) {
+    IeeeDiv dv;
+    return pair_production(K, q, p, T, dv);
+}
+NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab &T) {
+    IeeeDiv dv;
+    return photonuclear(K, q, p, T, dv);
+}
+NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &T) {
+    IeeeDiv dv;
+    return ionisation(K, q, p, T, dv);
+}
+
+template <int PROCESS, class DV>
+NOA_HD double dcs_eval(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
+    if (PROCESS == 0) return bremsstrahlung(K, q, p, T, dv);
+    if (PROCESS == 1) return pair_production(K, q, p, T, dv);
+    if (PROCESS == 2) return photonuclear(K, q, p, T, dv);
+    return ionisation(K, q, p, T, dv);
 }
 
 template <int PROCESS>
