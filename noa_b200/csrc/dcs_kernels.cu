@@ -90,21 +90,23 @@ struct StagedShared {
     double dens[kDenSlots];
 };
 
-__device__ __forceinline__ glibm::Tab stage_all(StagedShared &dst, const Params &p) {
-    if (threadIdx.x < kDenSlots) {
-        double b;
-        switch (threadIdx.x) {
-            case kDenLambda2: b = 0.06527; break;
-            case kDenQ004: b = 0.04; break;
-            case kDenLogQ0L: b = p.n_logq0l; break;
-            case kDenR2: b = p.p_r2; break;
-            case kDenA: b = p.A; break;
-            case kDenMass: b = p.mass; break;
-            case kDenMe: b = kElectronMass; break;
-            default: b = p.i_m2; break;
-        }
-        dst.dens[threadIdx.x] = FastDivT<true>::staged_reciprocal(b);
+__device__ __forceinline__ double den_slot_value(int slot, const Params &p) {
+    switch (slot) {
+        case kDenLambda2: return 0.06527;
+        case kDenQ004: return 0.04;
+        case kDenLogQ0L: return p.n_logq0l;
+        case kDenR2: return p.p_r2;
+        case kDenA: return p.A;
+        case kDenMass: return p.mass;
+        case kDenMe: return kElectronMass;
+        default: return p.i_m2;
     }
+}
+
+__device__ __forceinline__ glibm::Tab stage_all(StagedShared &dst, const Params &p) {
+    if (threadIdx.x < kDenSlots)
+        dst.dens[threadIdx.x] =
+                FastDivT<true>::staged_reciprocal(den_slot_value(threadIdx.x, p));
     glibm::Tab T = stage_tables(dst.tables);
     T.aux_smem = T.exp_smem + (uint32_t) offsetof(StagedShared, dens);
     return T;
@@ -241,11 +243,22 @@ __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, 
     }
 }
 
+// Tables + one set of staged reciprocals per element of the mixture
+struct MixtureShared {
+    glibm::Tables tables;
+    double dens[NOA_DCS_MAX_ELEMENTS][kDenSlots];
+};
+
 __global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
 vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
                     double *__restrict__ out, int64_t n, const __grid_constant__ Mixture m) {
-    __shared__ glibm::Tables s_tables;
-    const glibm::Tab T = stage_tables(s_tables);
+    __shared__ MixtureShared s_staged;
+    if (threadIdx.x < m.n_elements * kDenSlots) {
+        const int e = threadIdx.x / kDenSlots, slot = threadIdx.x % kDenSlots;
+        s_staged.dens[e][slot] = FastDivT<true>::staged_reciprocal(den_slot_value(slot, m.p[e]));
+    }
+    const glibm::Tab T0 = stage_tables(s_staged.tables);
+    const uint32_t dens0 = T0.exp_smem + (uint32_t) offsetof(MixtureShared, dens);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double k = K[i], r = q[i];
@@ -255,8 +268,11 @@ vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
             if (!((m.process_mask >> process) & 1u)) continue;
             double acc = 0.;
 #pragma unroll 1
-            for (int e = 0; e < m.n_elements; e++)
-                acc += m.w[e] * dcs_dispatch<false>(process, k, r, m.p[e], T);
+            for (int e = 0; e < m.n_elements; e++) {
+                glibm::Tab T = T0;
+                T.aux_smem = dens0 + (uint32_t) (e * kDenSlots * sizeof(double));
+                acc += m.w[e] * dcs_dispatch<true>(process, k, r, m.p[e], T);
+            }
             out[(int64_t) slot * n + i] = acc;
             slot++;
         }

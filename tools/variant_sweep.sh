@@ -1,4 +1,5 @@
 #!/bin/bash
+shopt -s nullglob
 # developer helper: run tools/quick_perf.py against every library build under variants/
 for lib in noa_b200/libnoa_dcs_b200.so variants/*.so; do
   echo "== $lib"
