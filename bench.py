@@ -209,7 +209,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -227,7 +227,27 @@ def workload_config(n_gpus):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+# The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL announces its
+# version on fd 1 when the box sets NCCL_DEBUG), so fd 1 is pointed at stderr for the whole run and
+# the result line goes to a private duplicate of the original stdout.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -420,7 +440,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "extras": extras,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if distributed:
         dist.destroy_process_group()
     return 0
