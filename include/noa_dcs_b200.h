@@ -254,7 +254,7 @@ int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t 
 /* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
 int64_t noa_dcs_launch_count(void);
 
-/* Diagnostics of the folded division checks (csrc/fdiv.cuh): how many DCS values on the current
+/* Diagnostics of the folded division checks (csrc/folded_ops.cuh): how many DCS values on the current
  * device had to be evaluated a second time with plain IEEE division because one of their
  * divisions left the fast-path domain (zero or subnormal-range numerator, non-finite operand).
  * Synchronises the device; `reset` != 0 clears the counter afterwards. */

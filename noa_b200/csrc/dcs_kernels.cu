@@ -75,7 +75,7 @@ __device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
     return glibm::make_smem_tab(dst);
 }
 
-// Evaluation of one DCS value with the folded division checks of fdiv.cuh: the FastDiv pass, and
+// Evaluation of one DCS value with the folded division checks of folded_ops.cuh: the FastDiv pass, and
 // -- only if one of its divisions left nvcc's fast-path domain (zero / subnormal-range numerator,
 // non-finite or out-of-range quotient) -- the same value again with plain IEEE division, out of
 // line.  g_div_recomputes counts those second passes (diagnostics: noa_dcs_div_recomputes).
@@ -84,7 +84,7 @@ __device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
 #endif
 __device__ unsigned long long g_div_recomputes = 0;
 
-// Tables plus the refined reciprocals of the launch-invariant denominators (fdiv.cuh: DenSlot).
+// Tables plus the refined reciprocals of the launch-invariant denominators (folded_ops.cuh: DenSlot).
 struct StagedShared {
     glibm::Tables tables;
     double dens[kDenSlots];
@@ -106,7 +106,7 @@ __device__ __forceinline__ double den_slot_value(int slot, const Params &p) {
 __device__ __forceinline__ glibm::Tab stage_all(StagedShared &dst, const Params &p) {
     if (threadIdx.x < kDenSlots)
         dst.dens[threadIdx.x] =
-                FastDivT<true>::staged_reciprocal(den_slot_value(threadIdx.x, p));
+                FoldedOps<true>::staged_reciprocal(den_slot_value(threadIdx.x, p));
     glibm::Tab T = stage_tables(dst.tables);
     T.aux_smem = T.exp_smem + (uint32_t) offsetof(StagedShared, dens);
     return T;
@@ -124,7 +124,7 @@ template <int PROCESS, bool STAGED>
 __device__ __forceinline__ double dcs_value(double K, double q, const Params &p,
                                             const glibm::Tab &T) {
 #if NOA_FAST_DIV
-    FastDivT<STAGED> dv;
+    FoldedOps<STAGED> dv;
     dv.dens = T.aux_smem;
     double v = dcs_eval<PROCESS>(K, q, p, T, dv);
     if (!dv.ok()) v = dcs_eval_ieee<PROCESS>(K, q, p, T);
@@ -255,7 +255,7 @@ vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
     __shared__ MixtureShared s_staged;
     if (threadIdx.x < m.n_elements * kDenSlots) {
         const int e = threadIdx.x / kDenSlots, slot = threadIdx.x % kDenSlots;
-        s_staged.dens[e][slot] = FastDivT<true>::staged_reciprocal(den_slot_value(slot, m.p[e]));
+        s_staged.dens[e][slot] = FoldedOps<true>::staged_reciprocal(den_slot_value(slot, m.p[e]));
     }
     const glibm::Tab T0 = stage_tables(s_staged.tables);
     const uint32_t dens0 = T0.exp_smem + (uint32_t) offsetof(MixtureShared, dens);

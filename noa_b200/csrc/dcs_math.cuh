@@ -6,7 +6,7 @@
 //   * sub-expressions that depend only on (element, projectile mass) are evaluated once on the
 //     host (dcs_params.hh) with the same operand order and handed over in `Params`;
 //   * exp/log/log10 are glibm:: (glibm.cuh), the table-driven routines glibc itself runs.
-// Division goes through a policy object (fdiv.cuh): IeeeDiv is the plain `/`; FastDiv (device
+// Division goes through a policy object (folded_ops.cuh): PlainOps is the plain `/`; FastDiv (device
 // only) is the same correctly-rounded quotient with the range checks of all divisions of one DCS
 // value folded into one flag.  sqrt is CUDA's IEEE-correct one.  The translation unit is compiled with
 // -fmad=false so that no multiply-add is contracted; the reference's benchmark/test builds
@@ -18,7 +18,7 @@
 #pragma once
 
 #include "glibm.cuh"
-#include "fdiv.cuh"
+#include "folded_ops.cuh"
 
 namespace noa_b200 {
 
@@ -100,12 +100,12 @@ NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::T
     const double qe_max = dv.div(E, 1. + dv.div(p.b_hm2, me * E));
     const double nu = dv.div(q, by_E);
     const double delta = dv.div(delta_factor * nu, 1. - nu);
-    double phi_n = glibm::log(dv.div(p.b_bzn * (p.mass + delta * p.b_c1),
+    double phi_n = dv.log(dv.div(p.b_bzn * (p.mass + delta * p.b_c1),
                                      p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
     if (phi_n < 0.) phi_n = 0.;
     double phi_e = 0.;
     if (q < qe_max) {
-        phi_e = glibm::log(dv.div(p.b_bzem,
+        phi_e = dv.log(dv.div(p.b_bzem,
                                   (1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
         if (phi_e < 0.) phi_e = 0.;
     }
@@ -134,7 +134,7 @@ NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tab &T,
     const double x1 = dv.div(6., k.gamma * (k.gamma - dv.div_slot(q, p.mass, kDenMass)));
     const double argmin = dv.div(x0 + 2. * (1. - x0) * x1, 1. + (1. - x1) * sqrt(1. - x0));
     if ((argmin >= 1.) || (argmin <= 0.)) return false;
-    k.tmin = glibm::log(argmin, T);
+    k.tmin = dv.log(argmin, T);
     return true;
 }
 
@@ -143,7 +143,7 @@ template <class DV>
 NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Params &p,
                         const glibm::Tab &T, DV &dv) {
     const double beta = k.beta;
-    const double eps = glibm::exp(t * k.tmin, T);
+    const double eps = dv.exp(t * k.tmin, T);
     const double rho = 1. - eps;
     const double rho2 = rho * rho;
     const double rho21 = eps * (2. - eps);
@@ -155,15 +155,15 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
     if (xi >= 1E+03)
         Be = 0.5 * xi_i * ((3 - rho2) + 2. * beta * (1. + rho2));
     else
-        Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) * glibm::log(1. + xi_i, T) +
+        Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) * dv.log(1. + xi_i, T) +
              dv.div(rho21 - beta, by_1xi) - 3. - rho2;
     const double Ye = dv.div(5. - rho2 + 4. * beta * (1. + rho2),
-                             2. * (1. + 3. * beta) * glibm::log(3. + xi_i, T) - rho2 -
+                             2. * (1. + 3. * beta) * dv.log(3. + xi_i, T) - rho2 -
                                      2. * beta * (2. - rho2));
     const double xe = (1. + xi) * (1. + Ye);
     const double cLi = dv.div(p.p_cl, rho21);
-    const double Le = glibm::log(dv.div(p.p_az13 * sqrt(xe) * q, q + cLi * xe), T) -
-                      0.5 * glibm::log(1. + p.p_cle * xe, T);
+    const double Le = dv.log(dv.div(p.p_az13 * sqrt(xe) * q, q + cLi * xe), T) -
+                      0.5 * dv.log(1. + p.p_cle * xe, T);
     double phi_e = Be * Le;
     if (phi_e < 0.) phi_e = 0.;
 
@@ -172,13 +172,13 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
         Bmu = 0.5 * xi * (5. - rho2 + beta * (3. + rho2));
     else
         Bmu = ((1. + rho2) * (1. + 1.5 * beta) - xi_i * (1. + 2. * beta) * rho21) *
-                      glibm::log(1. + xi, T) +
+                      dv.log(1. + xi, T) +
               dv.div(xi * (rho21 - beta), by_1xi) + (1. + 2. * beta) * rho21;
     const double Ymu = dv.div(4. + rho2 + 3. * beta * (1. + rho2),
-                              (1. + rho2) * (1.5 + 2. * beta) * glibm::log(3. + xi, T) + 1. -
+                              (1. + rho2) * (1.5 + 2. * beta) * dv.log(3. + xi, T) + 1. -
                                       1.5 * rho2);
     const double xmu = (1. + xi) * (1. + Ymu);
-    const double Lmu = glibm::log(dv.div(p.p_raz13 * q, p.p_z15 * (q + cLi * xmu)), T);
+    const double Lmu = dv.log(dv.div(p.p_raz13 * q, p.p_z15 * (q + cLi * xmu)), T);
     double phi_mu = Bmu * Lmu;
     if (phi_mu < 0.) phi_mu = 0.;
     return -(phi_e + dv.div_slot(phi_mu, p.p_r2, kDenR2)) * (1. - rho) * k.tmin;
@@ -193,12 +193,12 @@ NOA_HD double pair_finish(double K, double q, double integral, const PairKinemat
     if (gamma <= 35.)
         zeta = 0.;
     else {
-        zeta = 0.073 * glibm::log(dv.div(gamma, 1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
+        zeta = 0.073 * dv.log(dv.div(gamma, 1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
                0.26;
         if (zeta <= 0.)
             zeta = 0.;
         else
-            zeta = dv.div(zeta, 0.058 * glibm::log(dv.div(gamma, 1. + p.p_g2 * gamma * p.p_z13),
+            zeta = dv.div(zeta, 0.058 * dv.log(dv.div(gamma, 1. + p.p_g2 * gamma * p.p_z13),
                                                    T) - 0.14);
     }
     const double E = K + p.mass;
@@ -234,31 +234,32 @@ NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T,
     const double M2 = 0.8803505929;
 
     const double W2 = M2 + Q2 * (dv.rcp(x) - 1.0);
-    const double t = glibm::log(dv.div_slot(glibm::log(dv.div_slot(Q2 + Q02, Lambda2, kDenLambda2), T),
+    const double t = dv.log(dv.div_slot(dv.log(dv.div_slot(Q2 + Q02, Lambda2, kDenLambda2), T),
                                         p.n_logq0l, kDenLogQ0L), T);
     const double xP = dv.div(Q2 + mP2, Q2 + mP2 + W2 - M2);
     const double xR = dv.div(Q2 + mR2, Q2 + mR2 + W2 - M2);
-    const double lnt = glibm::log(t, T);
-    const double cP = cP1 + (cP1 - cP2) * (dv.rcp(1.0 + glibm::exp(cP3 * lnt, T)) - 1.0);
-    const double aP = aP1 + (aP1 - aP2) * (dv.rcp(1.0 + glibm::exp(aP3 * lnt, T)) - 1.0);
-    const double bP = bP1 + bP2 * glibm::exp(bP3 * lnt, T);
-    const double cR = cR1 + cR2 * glibm::exp(cR3 * lnt, T);
-    const double aR = aR1 + aR2 * glibm::exp(aR3 * lnt, T);
-    const double bR = bR1 + bR2 * glibm::exp(bR3 * lnt, T);
+    const double lnt = dv.log(t, T);
+    const double cP = cP1 + (cP1 - cP2) * (dv.rcp(1.0 + dv.exp(cP3 * lnt, T)) - 1.0);
+    const double aP = aP1 + (aP1 - aP2) * (dv.rcp(1.0 + dv.exp(aP3 * lnt, T)) - 1.0);
+    const double bP = bP1 + bP2 * dv.exp(bP3 * lnt, T);
+    const double cR = cR1 + cR2 * dv.exp(cR3 * lnt, T);
+    const double aR = aR1 + aR2 * dv.exp(aR3 * lnt, T);
+    const double bR = bR1 + bR2 * dv.exp(bR3 * lnt, T);
 
-    const double l1x = glibm::log(1 - x, T);
-    const double F2P = cP * glibm::exp(aP * glibm::log(xP, T) + bP * l1x, T);
-    const double F2R = cR * glibm::exp(aR * glibm::log(xR, T) + bR * l1x, T);
+    const double l1x = dv.log(1 - x, T);
+    const double F2P = cP * dv.exp(aP * dv.log(xP, T) + bP * l1x, T);
+    const double F2R = cR * dv.exp(aR * dv.log(xR, T) + bR * l1x, T);
     return dv.div(Q2, Q2 + m02) * (F2P + F2R);
 }
 
 // DRSS shadowing (dcs.hh:310-319)
-NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tab &T) {
+template <class DV>
+NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tab &T, DV &dv) {
     double a = 1.0;
     if (x < 0.0014)
         a = p.n_alow;
     else if (x < 0.04)
-        a = glibm::exp((0.069 * glibm::log10(x, T) + 0.097) * p.n_logA, T);
+        a = dv.exp((0.069 * dv.log10(x, T) + 0.097) * p.n_logA, T);
     return (p.n_halfA * a * (2.0 + x * (-1.85 + x * (2.45 + x * (-2.35 + x)))) * F2p);
 }
 
@@ -268,7 +269,7 @@ NOA_HD double r_whitlow(double x, double Q2, const glibm::Tab &T, DV &dv) {
     double q2 = Q2;
     if (Q2 < 0.3) q2 = 0.3;
     const double theta = 1 + dv.div(dv.div(12.0 * q2, 1.0 + q2) * 0.015625, 0.015625 + x * x);
-    return (dv.div(0.635, glibm::log(dv.div_slot(q2, 0.04, kDenQ004), T)) * theta + dv.div(0.5747, q2) -
+    return (dv.div(0.635, dv.log(dv.div_slot(q2, 0.04, kDenQ004), T)) * theta + dv.div(0.5747, q2) -
             dv.div(0.3534, 0.09 + q2 * q2));
 }
 
@@ -290,8 +291,8 @@ NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm:
     const double Q2min = dv.div(p.n_m2 * y * y, 1 - y);
     const double Q2max = 2.0 * M * (q - mpi) - mpi * mpi;
     if ((Q2max < Q2min) | (Q2min < 0)) return false;
-    const double lo = glibm::log(Q2min, T);
-    const double hi = glibm::log(Q2max, T);
+    const double lo = dv.log(Q2min, T);
+    const double hi = dv.log(Q2max, T);
     k.width = hi - lo;
     k.centre = 0.5 * (hi + lo);
     k.y = y;
@@ -306,11 +307,11 @@ template <class DV>
 NOA_HD double photonuclear_node(double t, const PhotoKinematics<DV> &k, const Params &p,
                                 const glibm::Tab &T, DV &dv) {
     const double cf = 2.603096E-35;
-    const double Q2 = glibm::exp(k.centre + 0.5 * k.width * t, T);
+    const double Q2 = dv.exp(k.centre + 0.5 * k.width * t, T);
     const double y = k.y;
     const double x = dv.div(0.5 * Q2, k.by_Mq);
     const double F2p = f2_allm(x, Q2, p, T, dv);
-    const double F2A = f2a_drss(x, F2p, p, T);
+    const double F2A = f2a_drss(x, F2p, p, T, dv);
     const double R = r_whitlow(x, Q2, T, dv);
     const double dds =
             dv.div(1 - y + dv.div(0.5 * (1 - dv.div(p.n_2m2, Q2)) * (y * y + dv.div(Q2, k.by_E2)),
@@ -353,9 +354,9 @@ NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &
                       (a0 + dv.div(1., by_q) * (a1 + dv.div(a2, by_q)));
     double Delta = 0.;
     if (K >= p.i_kthr) {
-        const double L1 = glibm::log(1. + dv.div_slot(2. * q, me, kDenMe), T);
+        const double L1 = dv.log(1. + dv.div_slot(2. * q, me, kDenMe), T);
         Delta = 1.16141E-03 * L1 *
-                (glibm::log(dv.div_slot(4. * E * (E - q), p.i_m2, kDenIm2), T) - L1);
+                (dv.log(dv.div_slot(4. * E * (E - q), p.i_m2, kDenIm2), T) - L1);
     }
     return cs * (1. + Delta);
 }
@@ -385,34 +386,34 @@ NOA_HD double ionisation_closed_form(double K, double xlow, int integrand, const
 
 // ---- plain-division forms (host build, table and Coulomb kernels, recompute path) -------------
 NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tab &T) {
-    IeeeDiv dv;
+    PlainOps dv;
     return bremsstrahlung(K, q, p, T, dv);
 }
 NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tab &T,
                        PairKinematics &k) {
-    IeeeDiv dv;
+    PlainOps dv;
     return pair_setup(K, q, p, T, k, dv);
 }
 NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Params &p,
                         const glibm::Tab &T) {
-    IeeeDiv dv;
+    PlainOps dv;
     return pair_node(t, q, k, p, T, dv);
 }
 NOA_HD double pair_finish(double K, double q, double integral, const PairKinematics &k,
                           const Params &p, const glibm::Tab &T) {
-    IeeeDiv dv;
+    PlainOps dv;
     return pair_finish(K, q, integral, k, p, T, dv);
 }
 NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T) {
-    IeeeDiv dv;
+    PlainOps dv;
     return pair_production(K, q, p, T, dv);
 }
 NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab &T) {
-    IeeeDiv dv;
+    PlainOps dv;
     return photonuclear(K, q, p, T, dv);
 }
 NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &T) {
-    IeeeDiv dv;
+    PlainOps dv;
     return ionisation(K, q, p, T, dv);
 }
 

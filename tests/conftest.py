@@ -66,7 +66,7 @@ def hostcheck():
     out = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
     src = os.path.join(ROOT, "oracle", "hostcheck.cc")
     deps = [src] + [os.path.join(ROOT, "noa_b200", "csrc", f)
-                    for f in ("dcs_math.cuh", "fdiv.cuh", "coulomb_math.cuh", "dcs_params.hh", "glibm.cuh",
+                    for f in ("dcs_math.cuh", "folded_ops.cuh", "coulomb_math.cuh", "dcs_params.hh", "glibm.cuh",
                               "glibm_tables.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
