@@ -221,56 +221,82 @@ NOA_HD double pair_production(double K, double q, const Params &p, const glibm::
 // ------------------------------------------------------------------------------------------
 // Photonuclear -- src/noa/pms/dcs.hh:261-405
 // ------------------------------------------------------------------------------------------
+// Literal constants of the photonuclear model.  On the device they sit in __constant__ memory: an
+// FP64 instruction takes an arbitrary 64-bit literal only through a uniform register, which costs
+// two UMOVs per use against one LDCU.64 from the constant bank (these kernels are bound by issue
+// slots; ~700 of the 9 300 instructions of a photonuclear value were such UMOVs).  Differences of
+// literals are folded here exactly as the reference's compiler folds them (IEEE double).
+struct PhotoConsts {
+    // ALLM97 (dcs.hh:262-287)
+    double m02, mP2, mR2, Q02, Lambda2, M2;
+    double cP1, cP1m2, cP3, aP1, aP1m2, aP3, bP1, bP2, bP3;
+    double cR1, cR2, cR3, aR1, aR2, aR3, bR1, bR2, bR3;
+    // DRSS shadowing (dcs.hh:312-318)
+    double x_lo, x_hi, s_a, s_b, s_c1, s_c2, s_c3;
+    // Whitlow R (dcs.hh:323-331)
+    double q2_min, w_c, w_q0, w_a, w_b, w_c2, w_d;
+    // d2sigma (dcs.hh:338)
+    double cf;
+};
+#define NOA_PHOTO_CONSTS_INIT                                                                     \
+    {0.31985, 49.457, 0.15052, 0.52544, 0.06527, 0.8803505929,                                    \
+     0.28067, 0.28067 - 0.22291, 2.1979, -0.0808, -0.0808 - -0.44812, 1.1709, 0.36292, 1.8917,    \
+     1.8439, 0.80107, 0.97307, 3.4942, 0.58400, 0.37888, 2.6063, 0.01147, 3.7582, 0.49338,        \
+     0.0014, 0.04, 0.069, 0.097, -1.85, 2.45, -2.35,                                              \
+     0.3, 0.015625, 0.04, 0.635, 0.5747, 0.09, 0.3534,                                            \
+     2.603096E-35}
+#if defined(__CUDACC__)
+__constant__ PhotoConsts c_photo = NOA_PHOTO_CONSTS_INIT;
+#endif
+static const PhotoConsts h_photo = NOA_PHOTO_CONSTS_INIT;
+#if defined(__CUDA_ARCH__)
+#define PK(name) (::noa_b200::c_photo.name)
+#else
+#define PK(name) (::noa_b200::h_photo.name)
+#endif
+
 // ALLM97 F2 (dcs.hh:261-307)
 template <class DV>
 NOA_HD double f2_allm(double x, double Q2, const Params &p, const glibm::Tab &T, DV &dv) {
-    const double m02 = 0.31985, mP2 = 49.457, mR2 = 0.15052, Q02 = 0.52544, Lambda2 = 0.06527;
-    const double cP1 = 0.28067, cP2 = 0.22291, cP3 = 2.1979;
-    const double aP1 = -0.0808, aP2 = -0.44812, aP3 = 1.1709;
-    const double bP1 = 0.36292, bP2 = 1.8917, bP3 = 1.8439;
-    const double cR1 = 0.80107, cR2 = 0.97307, cR3 = 3.4942;
-    const double aR1 = 0.58400, aR2 = 0.37888, aR3 = 2.6063;
-    const double bR1 = 0.01147, bR2 = 3.7582, bR3 = 0.49338;
-    const double M2 = 0.8803505929;
-
-    const double W2 = M2 + Q2 * (dv.rcp(x) - 1.0);
-    const double t = dv.log(dv.div_slot(dv.log(dv.div_slot(Q2 + Q02, Lambda2, kDenLambda2), T),
+    const double W2 = PK(M2) + Q2 * (dv.rcp(x) - 1.0);
+    const double t = dv.log(dv.div_slot(dv.log(dv.div_slot(Q2 + PK(Q02), PK(Lambda2), kDenLambda2),
+                                               T),
                                         p.n_logq0l, kDenLogQ0L), T);
-    const double xP = dv.div(Q2 + mP2, Q2 + mP2 + W2 - M2);
-    const double xR = dv.div(Q2 + mR2, Q2 + mR2 + W2 - M2);
+    const double xP = dv.div(Q2 + PK(mP2), Q2 + PK(mP2) + W2 - PK(M2));
+    const double xR = dv.div(Q2 + PK(mR2), Q2 + PK(mR2) + W2 - PK(M2));
     const double lnt = dv.log(t, T);
-    const double cP = cP1 + (cP1 - cP2) * (dv.rcp(1.0 + dv.exp(cP3 * lnt, T)) - 1.0);
-    const double aP = aP1 + (aP1 - aP2) * (dv.rcp(1.0 + dv.exp(aP3 * lnt, T)) - 1.0);
-    const double bP = bP1 + bP2 * dv.exp(bP3 * lnt, T);
-    const double cR = cR1 + cR2 * dv.exp(cR3 * lnt, T);
-    const double aR = aR1 + aR2 * dv.exp(aR3 * lnt, T);
-    const double bR = bR1 + bR2 * dv.exp(bR3 * lnt, T);
+    const double cP = PK(cP1) + PK(cP1m2) * (dv.rcp(1.0 + dv.exp(PK(cP3) * lnt, T)) - 1.0);
+    const double aP = PK(aP1) + PK(aP1m2) * (dv.rcp(1.0 + dv.exp(PK(aP3) * lnt, T)) - 1.0);
+    const double bP = PK(bP1) + PK(bP2) * dv.exp(PK(bP3) * lnt, T);
+    const double cR = PK(cR1) + PK(cR2) * dv.exp(PK(cR3) * lnt, T);
+    const double aR = PK(aR1) + PK(aR2) * dv.exp(PK(aR3) * lnt, T);
+    const double bR = PK(bR1) + PK(bR2) * dv.exp(PK(bR3) * lnt, T);
 
     const double l1x = dv.log(1 - x, T);
     const double F2P = cP * dv.exp(aP * dv.log(xP, T) + bP * l1x, T);
     const double F2R = cR * dv.exp(aR * dv.log(xR, T) + bR * l1x, T);
-    return dv.div(Q2, Q2 + m02) * (F2P + F2R);
+    return dv.div(Q2, Q2 + PK(m02)) * (F2P + F2R);
 }
 
 // DRSS shadowing (dcs.hh:310-319)
 template <class DV>
 NOA_HD double f2a_drss(double x, double F2p, const Params &p, const glibm::Tab &T, DV &dv) {
     double a = 1.0;
-    if (x < 0.0014)
+    if (x < PK(x_lo))
         a = p.n_alow;
-    else if (x < 0.04)
-        a = dv.exp((0.069 * dv.log10(x, T) + 0.097) * p.n_logA, T);
-    return (p.n_halfA * a * (2.0 + x * (-1.85 + x * (2.45 + x * (-2.35 + x)))) * F2p);
+    else if (x < PK(x_hi))
+        a = dv.exp((PK(s_a) * dv.log10(x, T) + PK(s_b)) * p.n_logA, T);
+    return (p.n_halfA * a * (2.0 + x * (PK(s_c1) + x * (PK(s_c2) + x * (PK(s_c3) + x)))) * F2p);
 }
 
 // Whitlow R (dcs.hh:322-332)
 template <class DV>
 NOA_HD double r_whitlow(double x, double Q2, const glibm::Tab &T, DV &dv) {
     double q2 = Q2;
-    if (Q2 < 0.3) q2 = 0.3;
-    const double theta = 1 + dv.div(dv.div(12.0 * q2, 1.0 + q2) * 0.015625, 0.015625 + x * x);
-    return (dv.div(0.635, dv.log(dv.div_slot(q2, 0.04, kDenQ004), T)) * theta + dv.div(0.5747, q2) -
-            dv.div(0.3534, 0.09 + q2 * q2));
+    if (Q2 < PK(q2_min)) q2 = PK(q2_min);
+    const double theta = 1 + dv.div(dv.div(12.0 * q2, 1.0 + q2) * PK(w_c), PK(w_c) + x * x);
+    return (dv.div(PK(w_a), dv.log(dv.div_slot(q2, PK(w_q0), kDenQ004), T)) * theta +
+            dv.div(PK(w_b), q2) - dv.div(PK(w_d), PK(w_c2) + q2 * q2));
 }
 
 template <class DV>
@@ -306,7 +332,6 @@ NOA_HD bool photonuclear_setup(double K, double q, const Params &p, const glibm:
 template <class DV>
 NOA_HD double photonuclear_node(double t, const PhotoKinematics<DV> &k, const Params &p,
                                 const glibm::Tab &T, DV &dv) {
-    const double cf = 2.603096E-35;
     const double Q2 = dv.exp(k.centre + 0.5 * k.width * t, T);
     const double y = k.y;
     const double x = dv.div(0.5 * Q2, k.by_Mq);
@@ -318,7 +343,7 @@ NOA_HD double photonuclear_node(double t, const PhotoKinematics<DV> &k, const Pa
                                   1 + R),
                    Q2 * Q2) -
             dv.div(0.25, k.by_E2.b * Q2);
-    return dv.div(cf * F2A * dds, k.by_q) * Q2;
+    return dv.div(PK(cf) * F2A * dds, k.by_q) * Q2;
 }
 
 template <class DV>
