@@ -61,6 +61,16 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def special():
+    """Zeros, subnormals, thresholds, q >= K, huge values, inf, NaN, negative energies -- outputs of
+    the compiled reference (tests/golden/make_special_golden.py)."""
+    return np.load(os.path.join(GOLDEN_DIR, "special_golden.npz"))
+
+
+SPECIAL_ELEMENTS = ("rock", "H", "Pb")
+
+
+@pytest.fixture(scope="session")
 def hostcheck():
     """Host build of the kernels' scalar arithmetic (test fixture, see oracle/hostcheck.cc)."""
     out = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")

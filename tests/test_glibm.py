@@ -43,3 +43,19 @@ def test_closed_form_ionisation_on_host(hostcheck, port):
                                                    ctypes.c_double(MUON_MASS))
         want = port.vmap_integral(3, ig, K, 0.05, 180, el, MUON_MASS)
         assert np.array_equal(out, want)
+
+
+def test_kernel_math_on_host_matches_reference_on_special_values(hostcheck, special):
+    from conftest import SPECIAL_ELEMENTS
+    K, q = special["S_K"], special["S_q"]
+    for en in SPECIAL_ELEMENTS:
+        el = ELEMENTS[en]
+        for p, pn in enumerate(("bremsstrahlung", "pair_production", "photonuclear", "ionisation")):
+            out = np.zeros_like(K)
+            rc = hostcheck.hostcheck_dcs(p, _p(K), _p(q), _p(out), ctypes.c_int64(K.size),
+                                         ctypes.c_double(el[0]), ctypes.c_double(el[1]),
+                                         ctypes.c_int32(el[2]), ctypes.c_double(MUON_MASS))
+            assert rc == 0
+            want = special[f"vmap_S_{en}_{pn}"]
+            bad = ~((out == want) | (np.isnan(out) & np.isnan(want)))
+            assert not bad.any(), (en, pn, K[bad][:4], q[bad][:4], out[bad][:4], want[bad][:4])

@@ -52,6 +52,46 @@ def test_vmap_against_golden(golden, grid):
             assert_parity(result, golden[f"vmap_{grid}_{en}_{pr.name}"], (grid, en, pr.name))
 
 
+def _same_values(got, want):
+    got = got.detach().cpu().numpy().reshape(-1)
+    return (got == want) | (np.isnan(got) & np.isnan(want))
+
+
+def test_special_values_follow_the_reference(special):
+    """Zeros, subnormals, the kinematic thresholds, q >= K, huge values, inf, NaN, negative energies
+    (tests/golden/make_special_golden.py): the kernels fold their division / exp / log special
+    cases into a flag and re-evaluate with the plain operations when it drops -- this is the input
+    set where that second path does all the work.  Same value, inf or NaN position everywhere."""
+    from conftest import SPECIAL_ELEMENTS
+    import ctypes
+    from noa_b200 import _lib
+    K, q = dev(special["S_K"]), dev(special["S_q"])
+    Kt = dev(special["ST_K"])
+    lib = _lib.require_device()
+    count = ctypes.c_int64(0)
+    _lib.check(lib.noa_dcs_div_recomputes(ctypes.byref(count), 1))
+    for en in SPECIAL_ELEMENTS:
+        el = ELEMENTS[en]
+        for pr in dcs.PROCESSES:
+            got = dcs.map(pr)(K, q, el, MUON_MASS)
+            ok = _same_values(got, special[f"vmap_S_{en}_{pr.name}"])
+            assert ok.all(), (en, pr.name, special["S_K"][~ok][:4], special["S_q"][~ok][:4],
+                              got.cpu().numpy()[~ok][:4], special[f"vmap_S_{en}_{pr.name}"][~ok][:4])
+            for ig in (dcs.del_integrand, dcs.cel_integrand):
+                res = torch.zeros_like(Kt)
+                dcs.vmap_integral(dcs.recoil_integral(pr, ig))(res, Kt, 0.05, el, MUON_MASS, 180)
+                want = special[f"integral_S_{en}_{pr.name}_{ig.name[:3]}_180"]
+                ok = _same_values(res, want)
+                assert ok.all(), (en, pr.name, ig.name, special["ST_K"][~ok],
+                                  res.cpu().numpy()[~ok], want[~ok])
+        # the fused forms see the same inputs
+        allp = dcs.cuda.map_all(K, q, el, MUON_MASS)
+        for pr in dcs.PROCESSES:
+            assert _same_values(allp[pr.index], special[f"vmap_S_{en}_{pr.name}"]).all(), (en, pr)
+    _lib.check(lib.noa_dcs_div_recomputes(ctypes.byref(count), 1))
+    assert count.value > 0      # the plain-operation path really ran
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100003])
 def test_vmap_ragged_sizes_against_oracle(port, n):
     K, q = grids.set_a(n)

@@ -115,3 +115,23 @@ def test_edge_cases(port):
     assert port.vmap(3, K, q, el, MUON_MASS)[1] == 0.0      # q > Wmax
     # NaN propagates through bremsstrahlung (no guard, physics.hh:135-152)
     assert np.isnan(port.vmap(0, np.array([np.nan]), np.array([1.0]), el, MUON_MASS)[0])
+
+
+def test_port_matches_reference_on_special_values(port, special):
+    """Inputs outside anything physical: the reference does not validate, so its 0 / NaN / inf /
+    garbage there is the contract (same NaN positions; NaN sign and payload are not compared)."""
+    from conftest import SPECIAL_ELEMENTS
+    K, q = special["S_K"], special["S_q"]
+    with np.errstate(all="ignore"):
+        for en in SPECIAL_ELEMENTS:
+            for p, pn in enumerate(PROC):
+                got = port.vmap(p, K, q, ELEMENTS[en], MUON_MASS)
+                want = special[f"vmap_S_{en}_{pn}"]
+                bad = ~((got == want) | (np.isnan(got) & np.isnan(want)))
+                assert not bad.any(), (en, pn, K[bad][:4], q[bad][:4], got[bad][:4], want[bad][:4])
+                for ig, ign in enumerate(("del", "cel")):
+                    got = port.vmap_integral(p, ig, special["ST_K"], 0.05, 180, ELEMENTS[en],
+                                             MUON_MASS)
+                    want = special[f"integral_S_{en}_{pn}_{ign}_180"]
+                    bad = ~((got == want) | (np.isnan(got) & np.isnan(want)))
+                    assert not bad.any(), (en, pn, ign, special["ST_K"][bad], got[bad], want[bad])
