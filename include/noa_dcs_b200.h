@@ -254,9 +254,10 @@ int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t 
 /* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
 int64_t noa_dcs_launch_count(void);
 
-/* Diagnostics of the folded division checks (csrc/folded_ops.cuh): how many DCS values on the current
- * device had to be evaluated a second time with plain IEEE division because one of their
- * divisions left the fast-path domain (zero or subnormal-range numerator, non-finite operand).
+/* Diagnostics of the folded special-case tests (csrc/folded_ops.cuh): how many DCS values on the
+ * current device had to be evaluated a second time with the plain operations because a division
+ * left the fast-path domain (zero or subnormal-range numerator, non-finite operand) or an exp / log
+ * argument left the common case.
  * Synchronises the device; `reset` != 0 clears the counter afterwards. */
 int noa_dcs_div_recomputes(int64_t *count, int reset);
 

@@ -75,12 +75,14 @@ __device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
     return glibm::make_smem_tab(dst);
 }
 
-// Evaluation of one DCS value with the folded division checks of folded_ops.cuh: the FastDiv pass, and
-// -- only if one of its divisions left nvcc's fast-path domain (zero / subnormal-range numerator,
-// non-finite or out-of-range quotient) -- the same value again with plain IEEE division, out of
-// line.  g_div_recomputes counts those second passes (diagnostics: noa_dcs_div_recomputes).
-#ifndef NOA_FAST_DIV
-#define NOA_FAST_DIV 1
+// Evaluation of one DCS value with the folded special-case tests of folded_ops.cuh: the FoldedOps
+// pass, and -- only if one of its divisions left nvcc's fast-path domain (zero / subnormal-range
+// numerator, non-finite or out-of-range quotient) or an exp / log argument left the common case --
+// the same value again with the plain operations, out of line.  g_div_recomputes counts those
+// second passes (diagnostics: noa_dcs_div_recomputes).  NOA_FOLDED_OPS=0 builds the kernels with
+// the plain operations only (measurement).
+#ifndef NOA_FOLDED_OPS
+#define NOA_FOLDED_OPS 1
 #endif
 __device__ unsigned long long g_div_recomputes = 0;
 
@@ -113,7 +115,7 @@ __device__ __forceinline__ glibm::Tab stage_all(StagedShared &dst, const Params 
 }
 
 template <int PROCESS>
-__device__ __noinline__ double dcs_eval_ieee(double K, double q, const Params &p,
+__device__ __noinline__ double dcs_eval_plain(double K, double q, const Params &p,
                                              const glibm::Tab &T) {
     atomicAdd(&g_div_recomputes, 1ULL);
     return dcs_eval<PROCESS>(K, q, p, T);
@@ -123,11 +125,11 @@ __device__ __noinline__ double dcs_eval_ieee(double K, double q, const Params &p
 template <int PROCESS, bool STAGED>
 __device__ __forceinline__ double dcs_value(double K, double q, const Params &p,
                                             const glibm::Tab &T) {
-#if NOA_FAST_DIV
+#if NOA_FOLDED_OPS
     FoldedOps<STAGED> dv;
     dv.dens = T.aux_smem;
     double v = dcs_eval<PROCESS>(K, q, p, T, dv);
-    if (!dv.ok()) v = dcs_eval_ieee<PROCESS>(K, q, p, T);
+    if (!dv.ok()) v = dcs_eval_plain<PROCESS>(K, q, p, T);
     return v;
 #else
     return dcs_eval<PROCESS>(K, q, p, T);

@@ -6,9 +6,10 @@
 //   * sub-expressions that depend only on (element, projectile mass) are evaluated once on the
 //     host (dcs_params.hh) with the same operand order and handed over in `Params`;
 //   * exp/log/log10 are glibm:: (glibm.cuh), the table-driven routines glibc itself runs.
-// Division goes through a policy object (folded_ops.cuh): PlainOps is the plain `/`; FastDiv (device
-// only) is the same correctly-rounded quotient with the range checks of all divisions of one DCS
-// value folded into one flag.  sqrt is CUDA's IEEE-correct one.  The translation unit is compiled with
+// Division, exp, log and log10 go through a policy object (folded_ops.cuh): PlainOps is the plain
+// `/` and glibm::exp / log / log10; FoldedOps (device only) produces the same values with the
+// special-case tests of all operations of one DCS value folded into one flag.  sqrt is CUDA's
+// IEEE-correct one.  The translation unit is compiled with
 // -fmad=false so that no multiply-add is contracted; the reference's benchmark/test builds
 // (-O3, x86-64 baseline) contain no FMA either.
 //
