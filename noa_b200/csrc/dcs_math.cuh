@@ -34,7 +34,7 @@ struct Params {
     int32_t Z;
     int32_t z_is_one;
     // bremsstrahlung (src/noa/pms/physics.hh:119-133)
-    double b_bzn, b_bze, b_dn, b_phie, b_pref, b_hm2, b_c1, b_bzem;
+    double b_bzn, b_bze, b_dn, b_phie, b_pref, b_hm2, b_c1, b_bzem, b_hm2me;
     // pair production (src/noa/pms/dcs.hh:153-166, 235-241, 255)
     double p_z13, p_thr, p_r, p_r2, p_hr2, p_az13, p_cl, p_cle, p_raz13, p_z15, p_g1, p_g2, p_cz;
     // photonuclear (src/noa/pms/dcs.hh:290, 313-315, 349, 374)
@@ -98,14 +98,15 @@ NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::T
     const double E = K + p.mass;
     const typename DV::Den by_E = dv.den(E);
     const double delta_factor = dv.div(p.b_hm2, by_E);
-    const double qe_max = dv.div(E, 1. + dv.div(p.b_hm2, me * E));
     const double nu = dv.div(q, by_E);
     const double delta = dv.div(delta_factor * nu, 1. - nu);
     double phi_n = dv.log(dv.div(p.b_bzn * (p.mass + delta * p.b_c1),
                                      p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
     if (phi_n < 0.) phi_n = 0.;
     double phi_e = 0.;
-    if (q < qe_max) {
+    // q < qe_max = E / (1 + hm2 / (me E)) (physics.hh:137, 146): qe_max is needed for nothing else,
+    // so the policy may decide the comparison without forming the two quotients
+    if (dv.below_ratio(q, E, by_E, p.b_hm2, me, p.b_hm2me)) {
         phi_e = dv.log(dv.div(p.b_bzem,
                                   (1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
         if (phi_e < 0.) phi_e = 0.;

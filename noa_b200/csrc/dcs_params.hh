@@ -31,6 +31,7 @@ inline Params make_params(double A, double I, int32_t Z, double mass) {
         p.b_dn = 1.54 * std::pow(A, 0.27);
         p.b_pref = 7.297182E-07 * rem * rem * Z;
         p.b_hm2 = 0.5 * mass * mass;
+        p.b_hm2me = p.b_hm2 / me;      // only used for an approximate pre-test (folded_ops.cuh)
         p.b_c1 = p.b_dn * sqrte - 2.;
         p.b_bzem = p.b_bze * mass;
     }

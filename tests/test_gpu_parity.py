@@ -92,6 +92,30 @@ def test_special_values_follow_the_reference(special):
     assert count.value > 0      # the plain-operation path really ran
 
 
+def test_bremsstrahlung_electron_term_threshold(port):
+    """The electron term of bremsstrahlung switches on at q < qe_max = E / (1 + m^2 / (2 me E))
+    (physics.hh:137, 146).  The kernel decides that comparison from an approximation and only forms
+    the quotients inside a 1e-12 band around the threshold: recoil energies ON the threshold, one
+    ulp either side and at relative distances from 1e-15 to 1e-9 must follow the reference."""
+    me = 0.510998910E-03
+    K = 10.0 ** np.linspace(-3, 7, 4001)
+    E = K + MUON_MASS
+    q0 = E / (1. + 0.5 * MUON_MASS * MUON_MASS / (me * E))
+    variants = [q0, np.nextafter(q0, 0.0), np.nextafter(q0, np.inf)]
+    for eps in (1e-15, 3e-15, 1e-14, 1e-13, 5e-13, 9.9e-13, 1.01e-12, 2e-12, 1e-11, 1e-9):
+        variants += [q0 * (1. - eps), q0 * (1. + eps)]
+    Kall = np.tile(K, len(variants))
+    qall = np.concatenate(variants)
+    for en in ("rock", "H", "Pb"):
+        got = dcs.map(dcs.bremsstrahlung)(dev(Kall), dev(qall), ELEMENTS[en], MUON_MASS)
+        want = port.vmap(0, Kall, qall, ELEMENTS[en], MUON_MASS, threads=8)
+        assert _same_values(got, want).all(), en
+        # the threshold really is inside the sample: both sides of the switch occur
+        on = port.vmap(0, K, variants[1], ELEMENTS[en], MUON_MASS)
+        off = port.vmap(0, K, variants[2], ELEMENTS[en], MUON_MASS)
+        assert np.any(on != off)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100003])
 def test_vmap_ragged_sizes_against_oracle(port, n):
     K, q = grids.set_a(n)
