@@ -88,31 +88,51 @@ static const double h_gl9_w[9] = NOA_GL9_W;
 #define NOA_GL(rule, what, j) h_gl##rule##_##what[j]
 #endif
 
+// Literal constants of bremsstrahlung and ionisation that do not fit an instruction's 32-bit
+// immediate: kept in __constant__ memory on the device (one LDCU.64 per use instead of two UMOVs,
+// see PhotoConsts below).  Products of literals are folded as the reference's compiler folds them.
+struct StreamConsts {
+    double me, two_me, sqrte_brems, four_thirds, avogadro, x_fraction, ion_pref, ion_rad;
+};
+#define NOA_STREAM_CONSTS_INIT                                                                   \
+    {0.510998910E-03, 2. * 0.510998910E-03, 1.648721271, 4. / 3., 6.02214076E+23, 5E-02,        \
+     1.535336E-05, 1.16141E-03}
+#if defined(__CUDACC__)
+__constant__ StreamConsts c_stream = NOA_STREAM_CONSTS_INIT;
+#endif
+static const StreamConsts h_stream = NOA_STREAM_CONSTS_INIT;
+#if defined(__CUDA_ARCH__)
+#define SK(name) (::noa_b200::c_stream.name)
+#else
+#define SK(name) (::noa_b200::h_stream.name)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // Bremsstrahlung -- src/noa/pms/physics.hh:114-153
 // ------------------------------------------------------------------------------------------
 template <class DV>
 NOA_HD double bremsstrahlung(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
-    const double me = kElectronMass;
-    const double sqrte = 1.648721271;
+    const double me = SK(me);
+    const double sqrte = SK(sqrte_brems);
     const double E = K + p.mass;
     const typename DV::Den by_E = dv.den(E);
     const double delta_factor = dv.div(p.b_hm2, by_E);
     const double nu = dv.div(q, by_E);
     const double delta = dv.div(delta_factor * nu, 1. - nu);
     double phi_n = dv.log(dv.div(p.b_bzn * (p.mass + delta * p.b_c1),
-                                     p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
+                                 p.b_dn * (me + delta * sqrte * p.b_bzn)), T);
     if (phi_n < 0.) phi_n = 0.;
     double phi_e = 0.;
     // q < qe_max = E / (1 + hm2 / (me E)) (physics.hh:137, 146): qe_max is needed for nothing else,
     // so the policy may decide the comparison without forming the two quotients
     if (dv.below_ratio(q, E, by_E, p.b_hm2, me, p.b_hm2me)) {
         phi_e = dv.log(dv.div(p.b_bzem,
-                                  (1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
+                              (1. + delta * p.b_phie) * (me + delta * sqrte * p.b_bze)), T);
         if (phi_e < 0.) phi_e = 0.;
     }
-    const double s = p.b_pref * (p.Zd * phi_n + phi_e) * (4. / 3. * (dv.rcp(nu) - 1.) + nu);
-    return (s < 0.) ? 0. : dv.div_slot(s * 1E+03 * kAvogadro, p.A, kDenA);
+    const double s = p.b_pref * (p.Zd * phi_n + phi_e) *
+                     (SK(four_thirds) * (dv.rcp(nu) - 1.) + nu);
+    return (s < 0.) ? 0. : dv.div_slot(s * 1E+03 * SK(avogadro), p.A, kDenA);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -366,23 +386,23 @@ NOA_HD double photonuclear(double K, double q, const Params &p, const glibm::Tab
 // ------------------------------------------------------------------------------------------
 template <class DV>
 NOA_HD double ionisation(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
-    const double me = kElectronMass;
+    const double me = SK(me);
     const double P2 = K * (K + 2. * p.mass);
     const double E = K + p.mass;
-    const double Wmax = dv.div(2. * me * P2, p.i_m2 + me * (me + 2. * E));
-    if ((Wmax < kXFraction * K) || (q > Wmax)) return 0.;
+    const double Wmax = dv.div(SK(two_me) * P2, p.i_m2 + me * (me + 2. * E));
+    if ((Wmax < SK(x_fraction) * K) || (q > Wmax)) return 0.;
     if (q <= p.i_wmin) return 0.;
     const typename DV::Den by_P2 = dv.den(P2);
     const double a0 = dv.div(0.5, by_P2);
     const double a1 = dv.div(-1., Wmax);
     const double a2 = dv.div(E * E, by_P2);
     const typename DV::Den by_q = dv.den(q);
-    const double cs = dv.div_slot(1.535336E-05 * E * p.Zd, p.A, kDenA) *
+    const double cs = dv.div_slot(SK(ion_pref) * E * p.Zd, p.A, kDenA) *
                       (a0 + dv.div(1., by_q) * (a1 + dv.div(a2, by_q)));
     double Delta = 0.;
     if (K >= p.i_kthr) {
         const double L1 = dv.log(1. + dv.div_slot(2. * q, me, kDenMe), T);
-        Delta = 1.16141E-03 * L1 *
+        Delta = SK(ion_rad) * L1 *
                 (dv.log(dv.div_slot(4. * E * (E - q), p.i_m2, kDenIm2), T) - L1);
     }
     return cs * (1. + Delta);
