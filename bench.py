@@ -172,6 +172,39 @@ def cpu_throughput(process, K, q, target_seconds, checker):
     return n / best, n, threads, spent, passes
 
 
+def cpu_table_sample(grids, n_sample=40):
+    """The reference's own table integrals (dcs::vmap_integral(recoil_integral), serial only:
+    dcs.hh:115-130) timed on a bounded sample of config 4: every 250th of the 10^4 energies, the
+    eight integrals each, 1000 points; plus the harness-side OpenMP loop over energies SURVEY 8(d)
+    asks for (on a sample large enough to keep every thread busy).  Scaled to the full table by
+    the sample fraction."""
+    checker, kind = load_cpu_checker()
+    grid = grids.table_energies(10000)
+
+    def run(K, threads):
+        t = time.perf_counter()
+        for process in range(4):
+            for integrand in (0, 1):
+                checker.vmap_integral(process, integrand, K, 0.05, 1000, ROCK, MUON_MASS,
+                                      threads=threads)
+        return (time.perf_counter() - t) * (grid.size / K.size)
+
+    Ks = grid[:: grid.size // n_sample].copy()
+    serial = run(Ks, 1)
+    threads = checker.max_threads
+    Kp = grid[:: max(1, grid.size // (64 * threads))].copy()
+    parallel = run(Kp, threads)
+    # the reference evaluates every node once per integrand: 8 x 1002 x n_K node evaluations
+    nodes = 8 * 1002 * grid.size
+    return {"kind": kind, "sample": f"serial: {Ks.size} of the 10^4 energies, OpenMP: {Kp.size}; "
+                                    "8 integrals each, 1000 points, scaled to the full table",
+            "serial_s_full_table": serial, "serial_evals_per_s": nodes / serial,
+            "omp_threads": threads, "omp_s_full_table": parallel,
+            "omp_evals_per_s": nodes / parallel,
+            "note": "reference is serial (dcs.hh:115-130); the OpenMP figure is a harness-side "
+                    "parallel loop over energies around the unmodified closure"}
+
+
 def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -518,6 +551,8 @@ def run_extras(torch, dist, dcs, grids, physics, lib, rank, world, distributed, 
             "includes": "every rank ends with the full [2,4,n_K] table" if world > 1
             else "single GPU"}
     del builders
+    if rank == 0 and world == 1:
+        out["table_build_1e4x1002"]["cpu_reference"] = cpu_table_sample(grids)
     # the rest of the dcs.hh surface: per-energy, latency-sized launches
     if rank == 0:
         n = Kt.numel()
