@@ -9,7 +9,7 @@
 //                           pair, shuffle gather, serial-order sum) -- kept for the measured
 //                           comparison in DESIGN.md
 //   vmap_all_kernel         the four processes of one pair in one pass (16 B in, 32 B out)
-//   vmap_mixture_kernel     sum_e w_e * DCS_e for the processes of a mask (water = H + O)
+//   vmap_mixture_element_kernel   one element's term of sum_e w_e * DCS_e (water = H + O)
 //   table_kernel            one CTA per (process, energy) row of the DEL/CEL tables: nodes of the
 //                           composite 6-point rule across threads, node terms staged in shared
 //                           memory and accumulated in the reference's serial order
@@ -215,13 +215,6 @@ vmap_all_kernel(const double *__restrict__ K, const double *__restrict__ q,
     }
 }
 
-struct Mixture {
-    int32_t n_elements;
-    uint32_t process_mask;
-    double w[NOA_DCS_MAX_ELEMENTS];
-    Params p[NOA_DCS_MAX_ELEMENTS];
-};
-
 template <bool STAGED>
 __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, const Params &p,
                                                const glibm::Tab &T) {
@@ -233,39 +226,38 @@ __device__ __forceinline__ double dcs_dispatch(int process, double k, double r, 
     }
 }
 
-// Tables + one set of staged reciprocals per element of the mixture
-struct MixtureShared {
-    glibm::Tables tables;
-    double dens[NOA_DCS_MAX_ELEMENTS][kDenSlots];
-};
-
+// One element of a mixture: out[slot * n + i] (+)= w * DCS_process(K[i], q[i]) for the processes of
+// the mask, slot counting the processes present.  A material is evaluated element by element,
+// one launch each (noa_dcs_vmap_mixture_f64): the element's Params then sit in the kernel
+// parameter bank at fixed offsets and its reciprocals are staged once per CTA exactly as in the
+// single-element kernels -- a kernel looping over the elements of a Mixture struct indexes the
+// constant bank with a register and was 9 % slower than the sum of its parts.  FIRST: the slot is
+// started as 0. + w * v, which is what `acc = 0.; acc += w * v` of the one-kernel form gives; the
+// later elements add in composition order, so the result is bit-identical to that form.
+template <bool FIRST>
 __global__ void __launch_bounds__(kThreads, NOA_MINB_ALL)
-vmap_mixture_kernel(const double *__restrict__ K, const double *__restrict__ q,
-                    double *__restrict__ out, int64_t n, const __grid_constant__ Mixture m) {
-    __shared__ MixtureShared s_staged;
-    if (threadIdx.x < m.n_elements * kDenSlots) {
-        const int e = threadIdx.x / kDenSlots, slot = threadIdx.x % kDenSlots;
-        s_staged.dens[e][slot] = FoldedOps<true>::staged_reciprocal(den_slot_value(slot, m.p[e]));
-    }
-    const glibm::Tab T0 = stage_tables(s_staged.tables);
-    const uint32_t dens0 = T0.exp_smem + (uint32_t) offsetof(MixtureShared, dens);
+vmap_mixture_element_kernel(const double *__restrict__ K, const double *__restrict__ q,
+                            double *__restrict__ out, int64_t n, uint32_t process_mask, double w,
+                            const __grid_constant__ Params p) {
+    __shared__ StagedShared s_staged;
+    const glibm::Tab T = stage_all(s_staged, p);
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double k = K[i], r = q[i];
-        int slot = 0;
-#pragma unroll 1
-        for (int process = 0; process < NOA_DCS_NPROCESS; process++) {
-            if (!((m.process_mask >> process) & 1u)) continue;
-            double acc = 0.;
-#pragma unroll 1
-            for (int e = 0; e < m.n_elements; e++) {
-                glibm::Tab T = T0;
-                T.aux_smem = dens0 + (uint32_t) (e * kDenSlots * sizeof(double));
-                acc += m.w[e] * dcs_dispatch<true>(process, k, r, m.p[e], T);
-            }
-            out[(int64_t) slot * n + i] = acc;
-            slot++;
+        double *o = out + i;
+        if (process_mask & 1u) {
+            *o = (FIRST ? 0. : *o) + w * dcs_value<0, true>(k, r, p, T);
+            o += n;
         }
+        if (process_mask & 2u) {
+            *o = (FIRST ? 0. : *o) + w * dcs_value<1, true>(k, r, p, T);
+            o += n;
+        }
+        if (process_mask & 4u) {
+            *o = (FIRST ? 0. : *o) + w * dcs_value<2, true>(k, r, p, T);
+            o += n;
+        }
+        if (process_mask & 8u) *o = (FIRST ? 0. : *o) + w * dcs_value<3, true>(k, r, p, T);
     }
 }
 
@@ -826,18 +818,21 @@ int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const doubl
     if (process_mask == 0 || process_mask > 15u || !A || !I || !Z || !w) return NOA_DCS_EINVAL;
     if (n == 0) return 0;
     if (!K || !q || !result) return NOA_DCS_EINVAL;
-    Mixture m{};
-    m.n_elements = n_elements;
-    m.process_mask = process_mask;
-    for (int e = 0; e < n_elements; e++) {
-        m.w[e] = w[e];
-        m.p[e] = make_params(A[e], I[e], Z[e], mass);
-    }
     int blocks = 0;
-    int rc = persistent_grid(vmap_mixture_kernel, n, blocks);
+    int rc = persistent_grid(vmap_mixture_element_kernel<true>, n, blocks);
     if (rc) return rc;
-    vmap_mixture_kernel<<<blocks, kThreads, 0, (cudaStream_t) stream>>>(K, q, result, n, m);
-    return after_launch();
+    for (int e = 0; e < n_elements; e++) {
+        const Params p = make_params(A[e], I[e], Z[e], mass);
+        if (e == 0)
+            vmap_mixture_element_kernel<true><<<blocks, kThreads, 0, (cudaStream_t) stream>>>(
+                    K, q, result, n, process_mask, w[e], p);
+        else
+            vmap_mixture_element_kernel<false><<<blocks, kThreads, 0, (cudaStream_t) stream>>>(
+                    K, q, result, n, process_mask, w[e], p);
+        rc = after_launch();
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
