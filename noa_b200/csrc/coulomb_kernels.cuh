@@ -82,13 +82,15 @@ hard_scattering_kernel(const double *__restrict__ G, const double *__restrict__ 
 __global__ void __launch_bounds__(kCoulombThreads)
 soft_scattering_kernel(const double *__restrict__ K, int64_t n, double *__restrict__ ms1,
                        const __grid_constant__ Params p, const __grid_constant__ CoulombParams c) {
-    __shared__ glibm::Tables s_tables;
+    __shared__ StagedShared s_staged;
     __shared__ double s_term[kSoftNodes];
-    const glibm::Tab T = stage_tables(s_tables);
+    const glibm::Tab T = stage_all(s_staged, p);
+    // the 102 photonuclear DCS values of a row with the folded special-case tests (folded_ops.cuh)
+    const auto photonuclear_dcs = [&](double kk, double qq) { return dcs_value<2, true>(kk, qq, p, T); };
     for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
         const double k = K[row];
         if (threadIdx.x < kSoftNodes)
-            s_term[threadIdx.x] = soft_photonuclear_term(threadIdx.x, k, p, c, T);
+            s_term[threadIdx.x] = soft_photonuclear_term(threadIdx.x, k, p, c, T, photonuclear_dcs);
         __syncthreads();
         if (threadIdx.x == 0) {
             double acc = 0.;

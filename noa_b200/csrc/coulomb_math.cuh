@@ -296,9 +296,11 @@ NOA_HD double transverse_transport_ionisation(double K, const Params &p, const C
                        a2 * glibm::log(mu3 / mu2, T));
 }
 
-// integrand of transverse_transport_photonuclear at node t, dcs.hh:909-936
+// integrand of transverse_transport_photonuclear at node t, dcs.hh:909-936; `dcs` evaluates
+// dcs::photonuclear(K, q) for this element (the kernel passes its folded-operations form)
+template <class PhotonuclearFn>
 NOA_HD double transverse_transport_photonuclear_node(double t, double K, const Params &p,
-                                                     const glibm::Tab &T) {
+                                                     const glibm::Tab &T, const PhotonuclearFn &dcs) {
     const double E = K + p.mass;
     const double nu = kXFraction * glibm::exp(t, T);
     const double q = nu * K;
@@ -318,18 +320,31 @@ NOA_HD double transverse_transport_photonuclear_node(double t, double K, const P
     L2 *= m02;
     const double I2 = (tmax - tmin) * (b1 * q2 + c1 * m02) - L1 - L2;
     const double ratio = (I1 * tmax - I2) / ((I0 * tmax - I1) * K * (K + 2. * p.mass));
-    return photonuclear(K, q, p, T) * ratio * nu;
+    return dcs(K, q) * ratio * nu;
 }
 
 constexpr int kSoftCells = (100 + 6 - 1) / 6;     // quadrature6(..., 100), numerics.hh:79
 constexpr int kSoftNodes = kSoftCells * 6;        // 102
 
 // term i of the composite rule: f(lb + h ((i / 6) + x_j)) h w_j   (numerics.hh:84-87)
-NOA_HD double soft_photonuclear_term(uint32_t i, double K, const Params &p,
-                                     const CoulombParams &c, const glibm::Tab &T) {
+template <class PhotonuclearFn>
+NOA_HD double soft_photonuclear_term(uint32_t i, double K, const Params &p, const CoulombParams &c,
+                                     const glibm::Tab &T, const PhotonuclearFn &dcs) {
     const uint32_t j = i % 6u;
     const double x = c.t_lb + c.t_h * ((i / 6u) + NOA_GL(6, x, j));
-    return transverse_transport_photonuclear_node(x, K, p, T) * c.t_h * NOA_GL(6, w, j);
+    return transverse_transport_photonuclear_node(x, K, p, T, dcs) * c.t_h * NOA_GL(6, w, j);
+}
+
+struct PlainPhotonuclear {      // dcs::photonuclear with the plain operations
+    const Params &p;
+    const glibm::Tab &T;
+    NOA_HD double operator()(double K, double q) const { return photonuclear(K, q, p, T); }
+};
+
+NOA_HD double soft_photonuclear_term(uint32_t i, double K, const Params &p,
+                                     const CoulombParams &c, const glibm::Tab &T) {
+    const PlainPhotonuclear dcs{p, T};
+    return soft_photonuclear_term(i, K, p, c, T, dcs);
 }
 
 }  // namespace noa_b200
