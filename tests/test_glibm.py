@@ -59,3 +59,19 @@ def test_kernel_math_on_host_matches_reference_on_special_values(hostcheck, spec
             want = special[f"vmap_S_{en}_{pn}"]
             bad = ~((out == want) | (np.isnan(out) & np.isnan(want)))
             assert not bad.any(), (en, pn, K[bad][:4], q[bad][:4], out[bad][:4], want[bad][:4])
+
+
+def test_kernel_math_on_host_with_tau_projectile(hostcheck, port):
+    """Every mass-dependent hoisted invariant (dcs_params.hh) with a projectile other than the
+    muon: tau, physics.hh:59."""
+    tau = 1.77682
+    for kind, (K, q) in (("A", grids.set_a(1 << 13)), ("B", grids.set_b(1 << 13))):
+        for en in ("rock", "H", "Pb"):
+            el = ELEMENTS[en]
+            for p in range(4):
+                out = np.zeros_like(K)
+                hostcheck.hostcheck_dcs(p, _p(K), _p(q), _p(out), ctypes.c_int64(K.size),
+                                        ctypes.c_double(el[0]), ctypes.c_double(el[1]),
+                                        ctypes.c_int32(el[2]), ctypes.c_double(tau))
+                want = port.vmap(p, K, q, el, tau, threads=4)
+                assert np.array_equal(out, want, equal_nan=True), (kind, en, p)

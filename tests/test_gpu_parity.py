@@ -295,6 +295,25 @@ def test_full_size_sample_against_oracle(port):
         assert_parity(full[torch.from_numpy(idx).cuda()], want, ("2^22 sample", pr.name))
 
 
+def test_tau_projectile(port):
+    """A projectile other than the muon (tau, physics.hh:59): every mass-dependent invariant and
+    staged reciprocal, element-wise and through the table integrals."""
+    tau = 1.77682
+    K, q = grids.set_a(1 << 15)
+    Kt = grids.table_energies(48, -2.0, 6.0)
+    for en in ("rock", "H", "Pb"):
+        for pr in dcs.PROCESSES:
+            got = dcs.map(pr)(dev(K), dev(q), ELEMENTS[en], tau)
+            assert_parity(got, port.vmap(pr.index, K, q, ELEMENTS[en], tau, threads=8),
+                          ("tau", en, pr.name))
+        d, c = dcs.cuda.tables(dev(Kt), dcs.X_FRACTION, ELEMENTS[en], tau, 180)
+        for pr in dcs.PROCESSES:
+            assert_parity(d[pr.index], port.vmap_integral(pr.index, 0, Kt, 0.05, 180, ELEMENTS[en],
+                                                          tau), ("tau DEL", en, pr.name))
+            assert_parity(c[pr.index], port.vmap_integral(pr.index, 1, Kt, 0.05, 180, ELEMENTS[en],
+                                                          tau), ("tau CEL", en, pr.name))
+
+
 def test_host_stager_roundtrip(port):
     K, q = grids.set_a(300001)
     Kh = torch.from_numpy(K).pin_memory()

@@ -47,6 +47,11 @@ def test_port_matches_compiled_reference(port, reference):
         a = port.vmap(p, K[:4096], q[:4096], ELEMENTS["rock"], 1.77682)
         b = reference.vmap(p, K[:4096], q[:4096], ELEMENTS["rock"], 1.77682)
         assert np.array_equal(a, b, equal_nan=True)
+        Kt = grids.table_energies(24, -2.0, 6.0)
+        for ig in (0, 1):
+            a = port.vmap_integral(p, ig, Kt, 0.05, 180, ELEMENTS["rock"], 1.77682)
+            b = reference.vmap_integral(p, ig, Kt, 0.05, 180, ELEMENTS["rock"], 1.77682)
+            assert np.array_equal(a, b, equal_nan=True), (p, ig)
 
 
 def test_notebook_printed_values(port):
