@@ -70,6 +70,22 @@ def special():
 SPECIAL_ELEMENTS = ("rock", "H", "Pb")
 
 
+def wild_inputs(n, seed=20261017):
+    """(K, q) with no physics in mind: half raw 64-bit patterns reinterpreted as doubles (NaNs,
+    infinities, subnormals, both signs), half log-uniform magnitudes over the whole double range
+    with a random sign.  Seeded; the reference's answer on them is whatever its arithmetic gives."""
+    rng = np.random.default_rng(seed)
+
+    def draw():
+        raw = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64).view(np.float64)
+        with np.errstate(all="ignore"):
+            mag = 10.0 ** rng.uniform(-320, 308, size=n) * rng.choice([-1.0, 1.0], size=n,
+                                                                      p=[0.1, 0.9])
+        return np.where(rng.random(n) < 0.5, raw, mag)
+
+    return draw(), draw()
+
+
 @pytest.fixture(scope="session")
 def hostcheck():
     """Host build of the kernels' scalar arithmetic (test fixture, see oracle/hostcheck.cc)."""

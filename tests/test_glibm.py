@@ -75,3 +75,18 @@ def test_kernel_math_on_host_with_tau_projectile(hostcheck, port):
                                         ctypes.c_int32(el[2]), ctypes.c_double(tau))
                 want = port.vmap(p, K, q, el, tau, threads=4)
                 assert np.array_equal(out, want, equal_nan=True), (kind, en, p)
+
+
+def test_kernel_math_on_host_on_wild_inputs(hostcheck, port):
+    from conftest import wild_inputs
+    K, q = wild_inputs(1 << 16)
+    for en in ("rock", "H"):
+        el = ELEMENTS[en]
+        for p in range(4):
+            out = np.zeros_like(K)
+            hostcheck.hostcheck_dcs(p, _p(K), _p(q), _p(out), ctypes.c_int64(K.size),
+                                    ctypes.c_double(el[0]), ctypes.c_double(el[1]),
+                                    ctypes.c_int32(el[2]), ctypes.c_double(MUON_MASS))
+            with np.errstate(all="ignore"):
+                want = port.vmap(p, K, q, el, MUON_MASS, threads=4)
+            assert ((out == want) | (np.isnan(out) & np.isnan(want))).all(), (en, p)

@@ -92,6 +92,30 @@ def test_special_values_follow_the_reference(special):
     assert count.value > 0      # the plain-operation path really ran
 
 
+def test_wild_inputs_follow_the_reference(port):
+    """2^18 (K, q) pairs of raw bit patterns and magnitudes from the whole double range (seeded,
+    conftest.wild_inputs): same value, inf or NaN position as the oracle for every process, also
+    through the fused and the host-buffer entry points."""
+    from conftest import wild_inputs
+    K, q = wild_inputs(1 << 18)
+    Kd, qd = dev(K), dev(q)
+    with np.errstate(all="ignore"):
+        want = [port.vmap(p, K, q, ELEMENTS["rock"], MUON_MASS, threads=8) for p in range(4)]
+    for pr in dcs.PROCESSES:
+        got = dcs.map(pr)(Kd, qd, ELEMENTS["rock"], MUON_MASS)
+        assert _same_values(got, want[pr.index]).all(), pr.name
+    allp = dcs.cuda.map_all(Kd, qd, ELEMENTS["rock"], MUON_MASS)
+    for pr in dcs.PROCESSES:
+        assert _same_values(allp[pr.index], want[pr.index]).all(), ("fused", pr.name)
+    st = dcs.HostStager()
+    try:
+        out = st.map(dcs.pair_production, torch.from_numpy(K).pin_memory(),
+                     torch.from_numpy(q).pin_memory(), ELEMENTS["rock"], MUON_MASS)
+        assert _same_values(out, want[1]).all()
+    finally:
+        st.close()
+
+
 def test_bremsstrahlung_electron_term_threshold(port):
     """The electron term of bremsstrahlung switches on at q < qe_max = E / (1 + m^2 / (2 me E))
     (physics.hh:137, 146).  The kernel decides that comparison from an approximation and only forms

@@ -140,3 +140,16 @@ def test_port_matches_reference_on_special_values(port, special):
                     want = special[f"integral_S_{en}_{pn}_{ign}_180"]
                     bad = ~((got == want) | (np.isnan(got) & np.isnan(want)))
                     assert not bad.any(), (en, pn, ign, special["ST_K"][bad], got[bad], want[bad])
+
+
+def test_port_matches_compiled_reference_on_wild_inputs(port, reference):
+    if reference is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    from conftest import wild_inputs
+    K, q = wild_inputs(1 << 16)
+    with np.errstate(all="ignore"):
+        for p in range(4):
+            for el in (ELEMENTS["rock"], ELEMENTS["H"]):
+                a = port.vmap(p, K, q, el, MUON_MASS, threads=4)
+                b = reference.vmap(p, K, q, el, MUON_MASS, threads=4)
+                assert ((a == b) | (np.isnan(a) & np.isnan(b))).all(), p
