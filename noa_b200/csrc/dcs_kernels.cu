@@ -50,10 +50,10 @@ constexpr int kThreads = NOA_THREADS;
 #define NOA_MINB_PHOTO 3
 #endif
 #ifndef NOA_MINB_STREAM
-#define NOA_MINB_STREAM 5
+#define NOA_MINB_STREAM 4
 #endif
 #ifndef NOA_MINB_ALL
-#define NOA_MINB_ALL 3
+#define NOA_MINB_ALL 2
 #endif
 #ifndef NOA_MINB_TABLE
 #define NOA_MINB_TABLE 4
