@@ -153,3 +153,16 @@ def test_port_matches_compiled_reference_on_wild_inputs(port, reference):
                 a = port.vmap(p, K, q, el, MUON_MASS, threads=4)
                 b = reference.vmap(p, K, q, el, MUON_MASS, threads=4)
                 assert ((a == b) | (np.isnan(a) & np.isnan(b))).all(), p
+
+
+def test_port_matches_compiled_reference_at_config_1_size(port, reference):
+    """BASELINE config 1 size (2^20 pairs) on both synthetic sets, standard rock: the restatement
+    and the compiled reference agree on every one of the 8 x 2^20 values."""
+    if reference is None:
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    n = 1 << 20
+    for K, q in (grids.set_a(n), grids.set_b(n)):
+        for p in range(4):
+            a = port.vmap(p, K, q, ELEMENTS["rock"], MUON_MASS, threads=8)
+            b = reference.vmap(p, K, q, ELEMENTS["rock"], MUON_MASS, threads=8)
+            assert np.array_equal(a, b, equal_nan=True), p
