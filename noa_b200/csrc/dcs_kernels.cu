@@ -39,12 +39,12 @@ constexpr int kThreads = NOA_THREADS;
 
 // Minimum resident CTAs per SM requested from ptxas (register cap = 65536 / (256 * N)).
 // The kernels are bound by issue slots and fixed-latency dependencies, not by the FP64 pipe alone
-// (profiles/), so occupancy matters; values chosen by measurement (gpurun sweep of
-// tools/variant_sweep.sh): pair/photonuclear 4 (64 registers), fused kernels 3,
-// table kernel 4 (a few spilled bytes are cheaper than a lost CTA).  The two streaming kernels
-// need < 50 registers anyway.
+// (profiles/), so occupancy matters; values chosen by measurement (tools/bounds_sweep.py,
+// profiles/r01_launch_bounds_sweep_s4.txt; all within ~1.5 % of each other except where noted):
+// pair 5 (48 registers), photonuclear 3 (80; 4 loses 4 %), streaming 4, fused four-process
+// kernels 2 (+2.7 % over 3), table kernel 4 (3 and 5 lose 4-6 %).
 #ifndef NOA_MINB_PAIR
-#define NOA_MINB_PAIR 4
+#define NOA_MINB_PAIR 5
 #endif
 #ifndef NOA_MINB_PHOTO
 #define NOA_MINB_PHOTO 3
