@@ -16,11 +16,19 @@
 //   default                            a minimal mirror of the types of src/noa/pms/physics.hh
 //                                      so the boundary builds without the reference present.
 //
-// Semantics: tensors must be CUDA, float64, contiguous, equal numel (checked; the reference
-// assumes it, src/noa/utils/common.cuh:45-56).  Work is enqueued on the current CUDA stream of the
-// tensors' device (the reference uses the legacy default stream) and is not synchronised.
-// `vmap_*` write `result` in place and never allocate; `map_*` return a fresh tensor shaped like
-// `kinetic_energies`.
+// Semantics: tensors must be float64, contiguous, equal numel, all on one device (checked; the
+// reference assumes it, src/noa/utils/common.cuh:45-56).
+//   * CUDA tensors: work is enqueued on the current CUDA stream of the tensors' device (the
+//     reference uses the legacy default stream) and is not synchronised.
+//   * CPU tensors (the reference's CPU call sites, dcs::vmap(f) on host memory,
+//     src/noa/pms/dcs.hh:35-60): evaluated on the current CUDA device through the host-buffer
+//     entry points of the C ABI -- pinned tensors are read and written in place by the kernel over
+//     PCIe, pageable ones go through a chunked copy pipeline -- and complete on return, like the
+//     CPU path they replace.  The element-wise and recoil-integral entry points and `tables` take
+//     them; the Coulomb entry points are CUDA-only.
+// `vmap_*` write `result` in place; `map_*` return a fresh tensor shaped like `kinetic_energies`.
+// include/noa_b200/pms_dcs.hh adds the reference's own CPU call SHAPES (dcs::vmap(dcs::f)(...),
+// dcs::vmap_integral(dcs::recoil_integral(f, g))(...)) on top of these.
 #pragma once
 
 #ifdef NOA_B200_WITH_REFERENCE_HEADERS
@@ -66,6 +74,15 @@ namespace noa::pms {
 #include <vector>
 
 namespace noa::pms::dcs::cuda {
+
+    // ---- by process id (0 bremsstrahlung, 1 pair_production, 2 photonuclear, 3 ionisation): what
+    // the named forms below and include/noa_b200/pms_dcs.hh forward to
+    void vmap_dcs(int process, const Calculation &result, const Energies &kinetic_energies,
+                  const Energies &recoil_energies, const AtomicElement &element,
+                  const ParticleMass &mass);
+    Calculation map_dcs(int process, const Energies &kinetic_energies,
+                        const Energies &recoil_energies, const AtomicElement &element,
+                        const ParticleMass &mass);
 
     // ---- same call shape as vmap_bremsstrahlung / map_bremsstrahlung for the other processes:
     // GPU forms of dcs::vmap(dcs::pair_production) etc. (src/noa/pms/dcs.hh:35-60, 144-443)

@@ -26,7 +26,8 @@
  *   noa_dcs_table_scatter_f64  the same for a cyclic shard of the energies, finished rows written
  *                              straight into every GPU's table over NVLink (no reference
  *                              counterpart: the reference is single-process)
- *   noa_dcs_table_exchange_f64 the same plus the rank barrier, all in one kernel launch
+ *   noa_dcs_table_exchange_f64 the same plus the rank barrier, inside the same launches
+ *   noa_dcs_allgather_f64      the NCCL all-gather of table slices SURVEY.md 8(b) proposes
  *   noa_dcs_vmap_host_f64      dcs::map(f) on CPU tensors           src/noa/pms/dcs.hh:50-60
  *                              (host buffers in, host buffers out; copies pipelined with compute)
  *   noa_dcs_vmap_pinned_f64    the same for pinned CPU tensors: one kernel streams the host arrays
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define NOA_DCS_ABI_VERSION 1
+#define NOA_DCS_ABI_VERSION 2
 
 /* process ids: PUMAS / NOA order (NPR = 4, src/noa/pms/physics.hh:86) */
 #define NOA_DCS_BREMSSTRAHLUNG 0
@@ -57,6 +58,11 @@ extern "C" {
 #define NOA_DCS_EINVAL (-1)  /* bad process id / mask / count / null pointer */
 #define NOA_DCS_ERANGE (-2)  /* size out of the supported range */
 #define NOA_DCS_ENODEV (-3)  /* no CUDA device: there is no CPU fallback */
+#define NOA_DCS_ENONCCL (-4) /* noa_dcs_allgather_f64: no NCCL in this process */
+#define NOA_DCS_ELIBM (-5)   /* noa_dcs_selfcheck: host libm is not the one the kernels restate */
+#define NOA_DCS_ENCCL_BASE (-1000) /* NCCL failure: code = NOA_DCS_ENCCL_BASE - ncclResult_t */
+
+#define NOA_DCS_DEFAULT_EXCHANGE_TIMEOUT_S 30.0
 
 int noa_dcs_abi_version(void);
 const char *noa_dcs_strerror(int code);
@@ -94,8 +100,10 @@ int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const doubl
  * i.e. composite 6-point Gauss-Legendre in ln q over [ln(K xlow), ln K] with
  * ceil(min_points / 6) cells, nodes accumulated in the reference's serial order, divided by
  * (K + mass); ionisation uses the closed form for K <= 0.5 (m - me)^2 / me.
- * del / cel are device arrays of 4 * nK doubles; rows of processes not in the mask are untouched.
- * Either may be NULL to skip that integrand.
+ * del / cel are device arrays of 4 * nK doubles; rows of processes not in the mask are set to
+ * zero.  Either may be NULL to skip that integrand.  A full build is four kernels (one per process,
+ * each with the register budget its integrand wants, chained with programmatic dependent launch
+ * so they overlap at their boundaries; work enqueued after the call sees all of them complete).
  */
 int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
                       int32_t min_points, double A, double I, int32_t Z, double mass, double *del,
@@ -131,24 +139,39 @@ int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int6
                               int64_t row_stride, void *stream);
 
 /*
- * noa_dcs_table_scatter_f64 with the rank synchronisation inside the same kernel: after its last
- * row is stored and fenced, the launch writes `epoch` into slot `my_peer` of every peer's flag
- * array (peer_flags[j] = peer j's array of n_peers 32-bit words, mapped here like the tables) and
- * returns only when all n_peers slots of its own array have reached `epoch`, i.e. when every
- * peer's rows have landed in this GPU's table.  One launch per rank builds, exchanges and
- * synchronises; work enqueued after it on `stream` sees the complete table.  `epoch` must increase
- * by one per call on all ranks (flags start at 0, first epoch 1); callers alternate between two
- * destination tables so a fast rank never overwrites rows a slow rank is still reading.
- * `done` = four zero-initialised 32-bit words on this device {CTA counter, timeout count, row
- * queue, reserved}; the second becomes non-zero if a peer did not arrive within about four seconds.
+ * noa_dcs_table_scatter_f64 with the rank synchronisation inside the same launches: after the last
+ * row of the build is stored and fenced, the build writes `epoch` into slot `my_peer` of every
+ * peer's flag array (peer_flags[j] = peer j's array of n_peers 32-bit words, mapped here like the
+ * tables) and returns only when all n_peers slots of its own array have reached `epoch`, i.e. when
+ * every peer's rows have landed in this GPU's table.  Persistent CTAs pull rows from a device-side
+ * queue, store finished values to all peers as they go and pay one system-scope fence each; work
+ * enqueued after the call on `stream` sees the complete table.  `epoch` must increase by one per
+ * call on all ranks (flags start at 0, first epoch 1); callers alternate between two destination
+ * tables so a fast rank never overwrites rows a slow rank is still reading.
+ * `sync` = EIGHT zero-initialised 32-bit words on this device {CTA counter, timeout count, 2
+ * reserved, 4 row queues}.  A peer that does not arrive within `timeout_seconds` of wall-clock time
+ * (<= 0: NOA_DCS_DEFAULT_EXCHANGE_TIMEOUT_S) is FATAL: the timeout count is bumped and the kernel
+ * traps, so the stream reports a launch failure instead of handing back a partial table.
  */
 int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int64_t n_local,
                                double xlow, int32_t min_points, double A, double I, int32_t Z,
                                double mass, int32_t n_peers, int32_t my_peer,
                                double *const *peer_del, double *const *peer_cel,
-                               uint32_t *const *peer_flags, uint32_t *done, uint32_t epoch,
+                               uint32_t *const *peer_flags, uint32_t *sync, uint32_t epoch,
                                int64_t n_total, int64_t first_row, int64_t row_stride,
-                               void *stream);
+                               double timeout_seconds, void *stream);
+
+/*
+ * The exchange SURVEY.md 8(b) sketches for hosts that hold an NCCL communicator instead of
+ * peer-mapped tables: in-place ncclAllGather (FP64) of `count_per_rank` doubles per rank, rank r's
+ * slice at table + r * count_per_rank, on `stream`.  `nccl_comm` is the caller's ncclComm_t.  NCCL
+ * is resolved at first use from what the process has loaded (no link-time dependency);
+ * NOA_DCS_ENONCCL if there is none, NOA_DCS_ENCCL_BASE - ncclResult_t on an NCCL error.
+ * With the cyclic row partition of the table builders the gathered layout is [rank][2][4][rows per
+ * rank]; noa_b200/sharding.py and examples/ show the un-permute.
+ */
+int noa_dcs_allgather_f64(double *table, int64_t count_per_rank, int32_t rank, void *nccl_comm,
+                          void *stream);
 
 /*
  * One column of the above, with the reference's own call shape
@@ -219,37 +242,20 @@ int noa_dcs_vmap_pinned_f64(int process, const double *h_K, const double *h_q, d
                             int64_t n, double A, double I, int32_t Z, double mass, void *stream);
 
 /*
- * Measurement helpers (bench.py): a dependent-chain-free DFMA loop used to measure the FP64-pipe
- * peak that the rooflines are quoted against.  Executes blocks * threads * iters * 16 DFMA.
+ * Host libm self-check.  Results are bit-identical to the reference's CPU path only when the
+ * host's exp / log / log10 / pow are the ones the device routines restate (glibc >= 2.28, FMA
+ * variant): this compares them on 3 x 1024 arguments plus pow known answers, entirely on the
+ * host.  Returns 0 when identical, NOA_DCS_ELIBM otherwise (`mismatches`, if not NULL, gets the
+ * count).  noa_b200/_lib.py runs it at load time and refuses to continue on a mismatch unless
+ * NOA_DCS_ALLOW_LIBM_MISMATCH=1.
  */
-int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink, void *stream);
-
-/* Same loop with other operand shapes, to measure what register-file bandwidth allows:
- * mode 0 = the probe above (DFMA, one register-pair source), 1 = DFMA with three distinct
- * register-pair sources, 2 = DFMA with two, 3 = DADD, 4 = DMUL; 5 / 6 / 7 = mode 0 with one / two /
- * three independent 32-bit integer multiply-adds issued per DFMA (do non-FP64 instructions issue in
- * the shadow of the half-rate FP64 dispatch, or do they take issue cycles of their own?);
- * 10 / 11 / 12 / 13 = 1 / 2 / 4 / 8 dependent DFMA chains per thread (still 16 DFMA per thread and
- * iteration): with one warp per scheduler the rate gives the dependent-issue latency. */
-int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t threads,
-                            double *sink, void *stream);
-
-/* Lane mapping of the pair-production kernel: 0 = one pair per thread (default), 1 = one
- * Gauss-Legendre node per lane (8 lanes per pair, shuffle gather).  Same results either way. */
-int noa_dcs_set_pair_mode(int mode);
-
-/* How noa_dcs_table_exchange_f64 runs (measurement hook): 3 = persistent CTAs pulling rows from a
- * device-side queue, one system fence per CTA (default); 0 / 1 / 2 = one CTA per row with the fence
- * after every writer lane's stores / once per CTA after the barrier / in the last CTA only (the
- * last one is for timing experiments: not a sufficient ordering). */
-int noa_dcs_set_exchange_fence_mode(int mode);
-
-/* Cap the resident CTAs per SM of the persistent element-wise kernels (0 = no cap; measurement hook
- * for occupancy-scaling experiments). */
-int noa_dcs_set_max_blocks_per_sm(int blocks);
+int noa_dcs_selfcheck(int64_t *mismatches);
 
 /* Launch geometry the element-wise kernels use on the current device (for reporting). */
 int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t *sm_count);
+
+/* Measurement kernels (FP64 pipe probes, the node-per-lane pair-production variant) are in a
+ * separate library: include/noa_dcs_b200_probe.h. */
 
 /* Number of kernels this library has launched since it was loaded (bench.py's gpu_launches). */
 int64_t noa_dcs_launch_count(void);

@@ -1,8 +1,12 @@
 """ctypes binding of the C ABI declared in include/noa_dcs_b200.h.
 
 The shared library is built in-tree (noa_b200/libnoa_dcs_b200.so, see noa_b200/csrc/Makefile).
-Loading fails loudly if it is missing; calling fails loudly if there is no CUDA device.  There is
-no fallback of any kind.
+Loading fails loudly if it is missing, or if the host libm is not the one the kernels restate
+(noa_dcs_selfcheck; NOA_DCS_ALLOW_LIBM_MISMATCH=1 turns that into a warning); calling fails loudly if
+there is no CUDA device.  There is no fallback of any kind.
+
+The measurement kernels (FP64 pipe probes, alternative lane mappings) are a separate library,
+noa_b200/libnoa_dcs_b200_probe.so (include/noa_dcs_b200_probe.h): `load_probe()`.
 """
 import ctypes
 import os
@@ -41,7 +45,8 @@ SIGNATURES = {
     "noa_dcs_table_exchange_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
                                                   _i32, _f64, _i32, _i32, ctypes.POINTER(_vp),
                                                   ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp,
-                                                  ctypes.c_uint32, _i64, _i64, _i64, _vp]),
+                                                  ctypes.c_uint32, _i64, _i64, _i64, _f64, _vp]),
+    "noa_dcs_allgather_f64": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "noa_dcs_vmap_integral_f64": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64, _f64,
                                                  _i32, _f64, _f64, _i32, _f64, _vp]),
     "noa_dcs_coulomb_data_f64": (ctypes.c_int, [_vp, _i64, _f64, _f64, _i32, _f64, _vp, _vp, _vp,
@@ -56,15 +61,22 @@ SIGNATURES = {
                                              _i32, _f64]),
     "noa_dcs_vmap_pinned_f64": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _i64, _f64, _f64, _i32,
                                                _f64, _vp]),
-    "noa_dcs_fp64_probe": (ctypes.c_int, [_i64, _i32, _i32, _vp, _vp]),
-    "noa_dcs_fp64_probe_mode": (ctypes.c_int, [_i32, _i64, _i32, _i32, _vp, _vp]),
-    "noa_dcs_set_pair_mode": (ctypes.c_int, [ctypes.c_int]),
-    "noa_dcs_set_exchange_fence_mode": (ctypes.c_int, [ctypes.c_int]),
-    "noa_dcs_set_max_blocks_per_sm": (ctypes.c_int, [ctypes.c_int]),
+    "noa_dcs_selfcheck": (ctypes.c_int, [ctypes.POINTER(_i64)]),
     "noa_dcs_launch_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_i32),
                                            ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "noa_dcs_launch_count": (_i64, []),
     "noa_dcs_div_recomputes": (ctypes.c_int, [ctypes.POINTER(_i64), ctypes.c_int]),
+}
+
+
+# include/noa_dcs_b200_probe.h
+PROBE_LIB_PATH = os.environ.get("NOA_DCS_PROBE_LIB") or os.path.join(_HERE,
+                                                                    "libnoa_dcs_b200_probe.so")
+PROBE_SIGNATURES = {
+    "noa_dcs_fp64_probe": (ctypes.c_int, [_i64, _i32, _i32, _vp, _vp]),
+    "noa_dcs_fp64_probe_mode": (ctypes.c_int, [_i32, _i64, _i32, _i32, _vp, _vp]),
+    "noa_dcs_probe_pair_lanes_f64": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f64, _f64, _i32, _f64,
+                                                    _vp]),
 }
 
 
@@ -73,6 +85,7 @@ class NoaDcsError(RuntimeError):
 
 
 _lib = None
+_probe = None
 
 
 def load():
@@ -90,9 +103,35 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.noa_dcs_abi_version() != 1:
+    if lib.noa_dcs_abi_version() != 2:
         raise NoaDcsError("libnoa_dcs_b200.so ABI version mismatch")
+    bad = _i64(0)
+    if lib.noa_dcs_selfcheck(ctypes.byref(bad)) != 0:
+        msg = (f"host libm differs from the glibc (>= 2.28, FMA variant) the kernels restate "
+               f"({bad.value} mismatches): results would no longer be bit-identical to the "
+               "reference's CPU path")
+        if os.environ.get("NOA_DCS_ALLOW_LIBM_MISMATCH") == "1":
+            import warnings
+            warnings.warn(msg)
+        else:
+            raise NoaDcsError(msg + " (set NOA_DCS_ALLOW_LIBM_MISMATCH=1 to continue anyway)")
     _lib = lib
+    return lib
+
+
+def load_probe():
+    """The measurement library (bench.py's FP64 peak probe, tools/)."""
+    global _probe
+    if _probe is not None:
+        return _probe
+    if not os.path.exists(PROBE_LIB_PATH):
+        raise NoaDcsError(f"{PROBE_LIB_PATH} is missing: build it with `make -C noa_b200/csrc`")
+    lib = ctypes.CDLL(PROBE_LIB_PATH)
+    for name, (res, args) in PROBE_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _probe = lib
     return lib
 
 

@@ -35,6 +35,7 @@ def main(force=False):
     link = ["-L" + tlib, "-L" + PKG, "-lnoa_dcs_b200", "-ltorch", "-ltorch_cpu", "-lc10",
             "-lc10_cuda", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tlib]
     hdr = [os.path.join(PKG, "..", "include", "noa_b200", "pms_dcs_cuda.hh"),
+           os.path.join(PKG, "..", "include", "noa_b200", "pms_dcs.hh"),
            os.path.join(PKG, "..", "include", "noa_dcs_b200.h")]
 
     api_src = os.path.join(HERE, "torch_api.cc")

@@ -1,144 +1,48 @@
 // B200 (sm_100a) kernels of the muon DCS hot path and the C ABI that exposes them
-// (include/noa_dcs_b200.h).  Torch-free on purpose: this file compiles in seconds and is the
-// whole product below the LibTorch boundary.
+// (include/noa_dcs_b200.h).  Torch-free on purpose: this file compiles in well under a minute and
+// is the whole product below the LibTorch boundary.
 //
 // Kernels
-//   vmap_kernel<P, VEC>     element-wise DCS of one process, one (K, q) pair per thread and
-//                           iteration, persistent grid-stride blocks, 128-bit loads/stores
-//   vmap_pair_lanes_kernel  pair production with one Gauss-Legendre node per lane (8 lanes per
-//                           pair, shuffle gather, serial-order sum) -- kept for the measured
-//                           comparison in DESIGN.md
+//   vmap_kernel<P, VEC>     element-wise DCS of one process, persistent grid-stride blocks; the two
+//                           streaming processes take 4 pairs per thread and iteration (two 128-bit
+//                           loads of K and of q issued before the first evaluation)
 //   vmap_all_kernel         the four processes of one pair in one pass (16 B in, 32 B out)
 //   vmap_mixture_element_kernel   one element's term of sum_e w_e * DCS_e (water = H + O)
-//   table_kernel            one CTA per (process, energy) row of the DEL/CEL tables: nodes of the
+//   table_kernel<MASK, PERSISTENT>  (table_kernels.cuh) rows of the DEL/CEL tables: nodes of the
 //                           composite 6-point rule across threads, node terms staged in shared
 //                           memory and accumulated in the reference's serial order
-//   fp64_probe_kernel       dependent-chain-free DFMA loop (roofline denominator)
+//   threshold / straggling  (material_kernels.cuh) the per-material table assembly of SURVEY 8(f1)
+//   coulomb_* / soft_scattering   (coulomb_kernels.cuh)
+// Measurement kernels (FP64 pipe probes, the node-per-lane pair-production variant) live in
+// probe_kernels.cu / libnoa_dcs_b200_probe.so, not here; this library keeps no mutable state
+// beyond a launch counter and the cached SM count.
 //
 // Numerics: FP64 throughout, every operation IEEE (see dcs_math.cuh, glibm.cuh); this file must be
 // compiled with -fmad=false.  The exp/log tables (4 KB) are staged into shared memory per CTA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <new>
 
 #include "../../include/noa_dcs_b200.h"
-#include "dcs_math.cuh"
+#include "dcs_device.cuh"
 #include "dcs_params.hh"
 
 namespace noa_b200 {
 
-__device__ const glibm::Tables g_tables = {GLIBM_EXP_TABLE_INIT, GLIBM_LOG_TABLE_INIT};
-
-#ifndef NOA_THREADS
-#define NOA_THREADS 256
-#endif
-constexpr int kThreads = NOA_THREADS;
-
-// Minimum resident CTAs per SM requested from ptxas (register cap = 65536 / (256 * N)).
-// The kernels are bound by issue slots and fixed-latency dependencies, not by the FP64 pipe alone
-// (profiles/), so occupancy matters; values chosen by measurement (tools/bounds_sweep.py,
-// profiles/r01_launch_bounds_sweep_s4.txt; all within ~1.5 % of each other except where noted):
-// pair 5 (48 registers), photonuclear 3 (80; 4 loses 4 %), streaming 4, fused four-process
-// kernels 2 (+2.7 % over 3), table kernel 4 (3 and 5 lose 4-6 %).
-#ifndef NOA_MINB_PAIR
-#define NOA_MINB_PAIR 5
-#endif
-#ifndef NOA_MINB_PHOTO
-#define NOA_MINB_PHOTO 3
-#endif
-#ifndef NOA_MINB_STREAM
-#define NOA_MINB_STREAM 4
-#endif
-#ifndef NOA_MINB_ALL
-#define NOA_MINB_ALL 2
-#endif
-#ifndef NOA_MINB_TABLE
-#define NOA_MINB_TABLE 4
-#endif
-template <int PROCESS>
-struct MinBlocks {
-    static constexpr int value = (PROCESS == 1) ? NOA_MINB_PAIR
-                                 : (PROCESS == 2) ? NOA_MINB_PHOTO : NOA_MINB_STREAM;
-};
-
-// 4 KB global -> shared, coalesced 128-bit copies; returns the shared-window addresses the
-// lookups use
-__device__ __forceinline__ glibm::Tab stage_tables(glibm::Tables &dst) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
-    uint4 *d = reinterpret_cast<uint4 *>(&dst);
-    for (int i = threadIdx.x; i < (int) (sizeof(glibm::Tables) / sizeof(uint4)); i += blockDim.x)
-        d[i] = src[i];
-    __syncthreads();
-    return glibm::make_smem_tab(dst);
-}
-
-// Evaluation of one DCS value with the folded special-case tests of folded_ops.cuh: the FoldedOps
-// pass, and -- only if one of its divisions left nvcc's fast-path domain (zero / subnormal-range
-// numerator, non-finite or out-of-range quotient) or an exp / log argument left the common case --
-// the same value again with the plain operations, out of line.  g_div_recomputes counts those
-// second passes (diagnostics: noa_dcs_div_recomputes).  NOA_FOLDED_OPS=0 builds the kernels with
-// the plain operations only (measurement).
-#ifndef NOA_FOLDED_OPS
-#define NOA_FOLDED_OPS 1
-#endif
-__device__ unsigned long long g_div_recomputes = 0;
-
-// Tables plus the refined reciprocals of the launch-invariant denominators (folded_ops.cuh: DenSlot).
-struct StagedShared {
-    glibm::Tables tables;
-    double dens[kDenSlots];
-};
-
-__device__ __forceinline__ double den_slot_value(int slot, const Params &p) {
-    switch (slot) {
-        case kDenLambda2: return 0.06527;
-        case kDenQ004: return 0.04;
-        case kDenLogQ0L: return p.n_logq0l;
-        case kDenR2: return p.p_r2;
-        case kDenA: return p.A;
-        case kDenMass: return p.mass;
-        case kDenMe: return kElectronMass;
-        default: return p.i_m2;
-    }
-}
-
-__device__ __forceinline__ glibm::Tab stage_all(StagedShared &dst, const Params &p) {
-    if (threadIdx.x < kDenSlots)
-        dst.dens[threadIdx.x] =
-                FoldedOps<true>::staged_reciprocal(den_slot_value(threadIdx.x, p));
-    glibm::Tab T = stage_tables(dst.tables);
-    T.aux_smem = T.exp_smem + (uint32_t) offsetof(StagedShared, dens);
-    return T;
-}
-
-template <int PROCESS>
-__device__ __noinline__ double dcs_eval_plain(double K, double q, const Params &p,
-                                             const glibm::Tab &T) {
-    atomicAdd(&g_div_recomputes, 1ULL);
-    return dcs_eval<PROCESS>(K, q, p, T);
-}
-
-// STAGED = T comes from stage_all() for this very `p`
-template <int PROCESS, bool STAGED>
-__device__ __forceinline__ double dcs_value(double K, double q, const Params &p,
-                                            const glibm::Tab &T) {
-#if NOA_FOLDED_OPS
-    FoldedOps<STAGED> dv;
-    dv.dens = T.aux_smem;
-    double v = dcs_eval<PROCESS>(K, q, p, T, dv);
-    if (!dv.ok()) v = dcs_eval_plain<PROCESS>(K, q, p, T);
-    return v;
-#else
-    return dcs_eval<PROCESS>(K, q, p, T);
-#endif
-}
-
 // ------------------------------------------------------------------------------------------
 // element-wise, one process
 // ------------------------------------------------------------------------------------------
+// VEC = pairs per thread and iteration: 1 (scalar loads; the quadrature-bound processes, whose
+// integrand is instantiated once), 2 (one double2 of K and of q) or 4 (two of each, all four loads
+// issued before the first evaluation: the streaming kernels were waiting on their own loads --
+// long_scoreboard 2.5 of 12 stall cycles per issue with VEC = 2, profiles/r01_ncu_full_s4c.md).
 template <int PROCESS, int VEC>
 __global__ void __launch_bounds__(kThreads, MinBlocks<PROCESS>::value)
 vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *__restrict__ out,
@@ -150,52 +54,47 @@ vmap_kernel(const double *__restrict__ K, const double *__restrict__ q, double *
     // K, q and out may also be pinned HOST buffers read and written in place over PCIe
     // (noa_dcs_vmap_pinned_f64); an explicit L2 prefetch of the next iteration's operands was
     // measured to gain nothing on either path and cost 3 % on the streaming kernels.
-    if (VEC == 2) {
+    if (VEC >= 2) {
         const int64_t n2 = n >> 1;
         const double2 *K2 = reinterpret_cast<const double2 *>(K);
         const double2 *q2 = reinterpret_cast<const double2 *>(q);
         double2 *o2 = reinterpret_cast<double2 *>(out);
-        for (int64_t i = tid; i < n2; i += stride) {
-            const double2 k = K2[i];
-            const double2 r = q2[i];
-            double2 o;
-            o.x = dcs_value<PROCESS, true>(k.x, r.x, p, T);
-            o.y = dcs_value<PROCESS, true>(k.y, r.y, p, T);
-            o2[i] = o;
+        if (VEC == 4) {
+            for (int64_t i = tid; i < n2; i += 2 * stride) {
+                const int64_t i1 = i + stride;
+                const bool two = i1 < n2;
+                const double2 k0 = K2[i];
+                const double2 r0 = q2[i];
+                double2 k1 = k0, r1 = r0;
+                if (two) {
+                    k1 = K2[i1];
+                    r1 = q2[i1];
+                }
+                double2 o;
+                o.x = dcs_value<PROCESS, true>(k0.x, r0.x, p, T);
+                o.y = dcs_value<PROCESS, true>(k0.y, r0.y, p, T);
+                o2[i] = o;
+                if (two) {
+                    o.x = dcs_value<PROCESS, true>(k1.x, r1.x, p, T);
+                    o.y = dcs_value<PROCESS, true>(k1.y, r1.y, p, T);
+                    o2[i1] = o;
+                }
+            }
+        } else {
+            for (int64_t i = tid; i < n2; i += stride) {
+                const double2 k = K2[i];
+                const double2 r = q2[i];
+                double2 o;
+                o.x = dcs_value<PROCESS, true>(k.x, r.x, p, T);
+                o.y = dcs_value<PROCESS, true>(k.y, r.y, p, T);
+                o2[i] = o;
+            }
         }
         if (tid == 0 && (n & 1)) out[n - 1] = dcs_value<PROCESS, true>(K[n - 1], q[n - 1], p, T);
     } else {
         for (int64_t i = tid; i < n; i += stride) {
             out[i] = dcs_value<PROCESS, true>(K[i], q[i], p, T);
         }
-    }
-}
-
-// pair production, one quadrature node per lane: lanes 8g..8g+7 of a warp share pair g.
-__global__ void __launch_bounds__(kThreads)
-vmap_pair_lanes_kernel(const double *__restrict__ K, const double *__restrict__ q,
-                       double *__restrict__ out, int64_t n, const __grid_constant__ Params p) {
-    __shared__ glibm::Tables s_tables;
-    const glibm::Tab T = stage_tables(s_tables);
-    const int lane = threadIdx.x & 31;
-    const int node = lane & 7;
-    const int64_t groups = ((int64_t) gridDim.x * blockDim.x) >> 3;
-    const int64_t g0 = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const int64_t rounds = (n + groups - 1) / groups;     // uniform trip count: shuffles are warp-wide
-    for (int64_t it = 0; it < rounds; it++) {
-        const int64_t i = g0 + it * groups;
-        const bool live = i < n;
-        const double k = live ? K[i] : 1.0;
-        const double r = live ? q[i] : 1.0;
-        PairKinematics kin;
-        const bool inside = live && pair_setup(k, r, p, T, kin);
-        double term = 0.;
-        if (inside) term = pair_node(c_gl8_x[node], r, kin, p, T) * c_gl8_w[node];
-        // gather the 8 node terms of the group and add them in node order (numerics.hh:84-87)
-        double acc = 0.;
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc += __shfl_sync(0xffffffffu, term, (lane & 24) | j);
-        if (live && node == 0) out[i] = inside ? pair_finish(k, r, acc, kin, p, T) : 0.;
     }
 }
 
@@ -212,17 +111,6 @@ vmap_all_kernel(const double *__restrict__ K, const double *__restrict__ q,
         out[n + i] = dcs_value<1, true>(k, r, p, T);
         out[2 * n + i] = dcs_value<2, true>(k, r, p, T);
         out[3 * n + i] = dcs_value<3, true>(k, r, p, T);
-    }
-}
-
-template <bool STAGED>
-__device__ __forceinline__ double dcs_dispatch(int process, double k, double r, const Params &p,
-                                               const glibm::Tab &T) {
-    switch (process) {
-        case 0: return dcs_value<0, STAGED>(k, r, p, T);
-        case 1: return dcs_value<1, STAGED>(k, r, p, T);
-        case 2: return dcs_value<2, STAGED>(k, r, p, T);
-        default: return dcs_value<3, STAGED>(k, r, p, T);
     }
 }
 
@@ -261,345 +149,11 @@ vmap_mixture_element_kernel(const double *__restrict__ K, const double *__restri
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// energy-loss tables: dcs::vmap_integral(dcs::recoil_integral(f, del|cel_integrand))
-// (src/noa/pms/dcs.hh:89-130, 955-1001; src/noa/utils/numerics.hh:72-108)
-// ------------------------------------------------------------------------------------------
-constexpr int kTableChunk = 1536;   // node terms staged per pass: 2 x 12 KB of shared memory
+}  // namespace noa_b200
 
-// Where the finished rows go: `n_peers` destination tables (this GPU's own and, in the multi-GPU
-// build, every peer's, mapped over NVLink), each [4][n_total]; local row r is global row
-// first_row + r * row_stride.
-struct TableOut {
-    int32_t n_peers;
-    int32_t me;               // index of this GPU among the peers (exchange form only)
-    int64_t n_total;
-    int64_t first_row;
-    int64_t row_stride;
-    double *del[NOA_DCS_MAX_PEERS];
-    double *cel[NOA_DCS_MAX_PEERS];
-    // exchange form (noa_dcs_table_exchange_f64): flags[j] = peer j's array of n_peers epoch words,
-    // done = this GPU's CTA counter {count, timeouts}; flags[0] == nullptr otherwise
-    uint32_t *flags[NOA_DCS_MAX_PEERS];
-    uint32_t *done;
-    uint32_t epoch;
-    int32_t fence_mode;       // see g_exchange_fence_mode
-};
+#include "table_kernels.cuh"
 
-// Tail of the exchange form.  Every CTA has stored its values (local + peers) and fenced them at
-// system scope; the last CTA of the grid to get here publishes this GPU's epoch into every peer's
-// flag array (release, system scope) and then waits until every peer's epoch has arrived in its own
-// -- so when the kernel retires, the complete table is in this GPU's memory.  No host round trip,
-// no separate barrier kernel.  A peer that never shows up is reported, not waited for forever.
-__device__ __forceinline__ void table_exchange_tail(const TableOut &out) {
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    if (out.fence_mode == 1 || out.fence_mode == 3) __threadfence_system(); else __threadfence();
-    const uint32_t arrived = atomicAdd(out.done, 1u);
-    if (arrived != gridDim.x - 1) return;
-    out.done[0] = 0;                       // re-armed for the next launch on this stream
-    out.done[2] = 0;                       // (row queue of the persistent form)
-    __threadfence_system();
-    for (int j = 0; j < out.n_peers; j++)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(out.flags[j] + out.me),
-                     "r"(out.epoch)
-                     : "memory");
-    const long long t0 = clock64();
-    for (int j = 0; j < out.n_peers; j++) {
-        const uint32_t *slot = out.flags[out.me] + j;
-        for (;;) {
-            uint32_t seen;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(slot) : "memory");
-            if ((int32_t) (seen - out.epoch) >= 0) break;
-            if (clock64() - t0 > (1LL << 33)) {      // ~4 s at 1.965 GHz: a peer is missing
-                atomicAdd(out.done + 1, 1u);
-                return;
-            }
-            __nanosleep(100);
-        }
-    }
-}
-
-struct TablePlan {
-    int32_t n_slots;          // processes to build
-    int32_t process[4];       // heaviest first, so the tail of the grid is cheap rows
-    int32_t out_row[4];       // output row of process p (p for full tables, 0 for a single column)
-    uint32_t cells;           // ceil(min_points / 6)
-    double xlow;
-};
-
-// One (process, energy) row: item b of the heavy-first ordering.  Called by every thread of the
-// CTA; s_del / s_cel are free to overwrite on entry.  Stores are NOT fenced here.
-// Out of line on purpose: as its own function the row body is register-allocated on its own
-// (216 B of spills instead of 440 B when inlined into the persistent loop) -- measured 7 % faster
-// on the 180-point build and 3 % on the persistent exchange kernel (profiles/).
-#ifndef NOA_TABLE_ROW_INLINE
-#define NOA_TABLE_ROW_INLINE __noinline__
-#endif
-__device__ NOA_TABLE_ROW_INLINE void table_row(int64_t b, const double *__restrict__ K, int64_t nK,
-                                          const TableOut &out, const TablePlan &plan,
-                                          const Params &p, const glibm::Tab &T, double *s_del,
-                                          double *s_cel, uint32_t *queue = nullptr,
-                                          uint32_t *s_next = nullptr) {
-    // Persistent form only (queue != nullptr): lane 64, idle while lanes 0 / 32 add the node terms
-    // up, pops the CTA's next row at that point -- late enough that a heavy row in flight never
-    // sits on a row another CTA could have started (a pop at row start cost 17 % at 8 GPUs),
-    // early enough that the atomic's round trip is hidden behind the summation.
-    const int process = plan.process[b / nK];
-    const int64_t row = nK - 1 - (b % nK);
-    const double k = K[row];
-    const int tid = threadIdx.x;
-
-    // destination index and the lane that owns each integrand (lane 0: DEL, lane 32: CEL)
-    const int64_t at = (int64_t) plan.out_row[process] * out.n_total + out.first_row +
-                       row * out.row_stride;
-    double *const *dst = (tid == 0) ? out.del : out.cel;
-    const bool writer = (tid == 0 || tid == 32) && dst[0] != nullptr;
-
-    if (process == 3 && k <= p.i_kthr) {          // dcs.hh:963-966, 987-990
-        if (writer) {
-            const double v = ionisation_closed_form(k, plan.xlow, tid == 0 ? 0 : 1, p, T);
-            for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
-        }
-        if (queue != nullptr && tid == 64) *s_next = atomicAdd(queue, 1u);
-        return;
-    }
-
-    const double lb = glibm::log(k * plan.xlow, T);
-    const double ub = glibm::log(k, T);
-    const double h = (ub - lb) / plan.cells;
-    const uint32_t total = plan.cells * 6u;
-    double acc = 0.;
-    for (uint32_t base = 0; base < total; base += kTableChunk) {
-        const uint32_t count = min((uint32_t) kTableChunk, total - base);
-        for (uint32_t i = base + tid; i < base + count; i += kThreads) {
-            const uint32_t j = i % 6u;
-            const double x = lb + h * ((i / 6u) + c_gl6_x[j]);
-            const double r = glibm::exp(x, T);
-            const double f = dcs_dispatch<true>(process, k, r, p, T);
-            const double w = c_gl6_w[j];
-            const double fr = f * r;
-            s_del[i - base] = fr * h * w;           // del_integrand, dcs.hh:107-109
-            s_cel[i - base] = fr * r * h * w;       // cel_integrand, dcs.hh:111-113
-        }
-        __syncthreads();
-        // res += term, strictly in node order (numerics.hh:84-87): one lane per integrand
-        if (tid == 0) {
-            for (uint32_t i = 0; i < count; i++) acc += s_del[i];
-        } else if (tid == 32) {
-            for (uint32_t i = 0; i < count; i++) acc += s_cel[i];
-        } else if (tid == 64 && queue != nullptr && base + kTableChunk >= total) {
-            *s_next = atomicAdd(queue, 1u);
-        }
-        __syncthreads();
-    }
-    if (writer) {
-        const double v = acc / (k + p.mass);
-        // one store per destination: the local table and, over NVLink, each peer's copy
-        for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
-    }
-}
-
-// One CTA per row (local tables, and the scatter / per-row exchange forms).
-__global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
-table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
-             const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
-    __shared__ StagedShared s_staged;
-    __shared__ double s_del[kTableChunk];
-    __shared__ double s_cel[kTableChunk];
-    const glibm::Tab T = stage_all(s_staged, p);
-    table_row(blockIdx.x, K, nK, out, plan, p, T, s_del, s_cel);
-    // the writer lanes fence their own remote stores (fence_mode 0)
-    if (out.n_peers > 1 && out.fence_mode == 0 && (threadIdx.x == 0 || threadIdx.x == 32))
-        __threadfence_system();
-    if (out.flags[0] != nullptr && out.fence_mode != 4) table_exchange_tail(out);
-}
-
-// Persistent form of the exchange: a grid that fills the GPU once; every CTA pulls rows from a
-// device-side queue (out.done[2]) in the same heavy-first order, streams the finished values to
-// all peers as it goes, and pays for ONE system-scope fence at the very end -- a fence per row
-// costs ~7 us of CTA residency each (measured, profiles/), i.e. 8 % of the whole build.
-__global__ void __launch_bounds__(kThreads, NOA_MINB_TABLE)
-table_exchange_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
-                      const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
-    __shared__ StagedShared s_staged;
-    __shared__ double s_del[kTableChunk];
-    __shared__ double s_cel[kTableChunk];
-    __shared__ uint32_t s_item[2];
-    const glibm::Tab T = stage_all(s_staged, p);
-    const uint32_t total = (uint32_t) (nK * plan.n_slots);
-    if (threadIdx.x == 64) s_item[0] = atomicAdd(out.done + 2, 1u);
-    for (int cur = 0;; cur ^= 1) {
-        __syncthreads();                       // s_item[cur] written; node buffers free again
-        const uint32_t b = s_item[cur];
-        if (b >= total) break;
-        table_row(b, K, nK, out, plan, p, T, s_del, s_cel, out.done + 2, &s_item[cur ^ 1]);
-    }
-    table_exchange_tail(out);
-}
-
-// Material tables: out[c] = sum_e parts[e][c] * w[e], e in composition order, starting from 0
-// (the per-element mixing of src/noa/3rdparty/_pumas/pumas.c:8054-8078).  `columns` = 8 n_K.
-struct MixWeights {
-    int32_t n_elements;
-    double w[NOA_DCS_MAX_ELEMENTS];
-};
-
-__global__ void mix_tables_kernel(const double *__restrict__ parts, double *__restrict__ out,
-                                  int64_t columns, const __grid_constant__ MixWeights m) {
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < columns; c += stride) {
-        double acc = 0.;
-        for (int e = 0; e < m.n_elements; e++) acc += parts[(int64_t) e * columns + c] * m.w[e];
-        out[c] = acc;
-    }
-}
-
-// A rank with no rows of its own still has to take part in the exchange.
-__global__ void table_signal_kernel(const __grid_constant__ TableOut out) {
-    table_exchange_tail(out);
-}
-
-// ------------------------------------------------------------------------------------------
-// FP64 peak probe: 16 independent chains per thread.
-//   mode 0  DFMA a = a * const + const     (1 register-pair source)  -> the roofline denominator
-//   mode 1  DFMA a = a * b + c             (3 distinct register-pair sources)
-//   mode 2  DFMA a = a * b + const         (2 register-pair sources)
-//   mode 3  DADD a = a + b,  mode 4  DMUL a = a * b
-// Modes 1-4 exist to measure how register-file bandwidth limits real instruction mixes.
-// ------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void fp64_probe_kernel(int64_t iters, double *sink) {
-    double a[16], b[4], c[4];
-#pragma unroll
-    for (int j = 0; j < 16; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        b[j] = 0.999999 + 1e-9 * (threadIdx.x + j);
-        c[j] = 1e-6 + 1e-12 * (threadIdx.x + j);
-    }
-    const double kb = 0.999999, kc = 1e-6;
-    for (int64_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (MODE == 0) a[j] = fma(a[j], kb, kc);
-            if (MODE == 1) a[j] = fma(a[j], b[j & 3], c[(j >> 2) & 3]);
-            if (MODE == 2) a[j] = fma(a[j], b[j & 3], kc);
-            if (MODE == 3) a[j] = __dadd_rn(a[j], c[j & 3]);
-            if (MODE == 4) a[j] = __dmul_rn(a[j], b[j & 3]);
-        }
-    }
-    double s = 0.;
-#pragma unroll
-    for (int j = 0; j < 16; j++) s += a[j];
-    if (s == 123456.789) sink[0] = s;   // never true; keeps the chains alive
-}
-
-// Latency probe: CHAINS independent dependent-DFMA chains per thread (mode 0 is CHAINS = 16).
-template <int CHAINS>
-__global__ void fp64_chain_probe_kernel(int64_t iters, double *sink) {
-    double a[CHAINS];
-#pragma unroll
-    for (int j = 0; j < CHAINS; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
-    const double kb = 0.999999, kc = 1e-6;
-    for (int64_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 16 / CHAINS; r++)
-#pragma unroll
-            for (int j = 0; j < CHAINS; j++) a[j] = fma(a[j], kb, kc);
-    }
-    double s = 0.;
-#pragma unroll
-    for (int j = 0; j < CHAINS; j++) s += a[j];
-    if (s == 123456.789) sink[0] = s;
-}
-
-// Constant-load probe: dependent DFMA chains (CHAINS per thread) whose multiplier is re-read from
-// the constant bank before every DFMA (ld.const through the LDC / IDC path, as the polynomial
-// coefficients of glibm are), to see what a constant load in the dependency chain costs.
-__constant__ double c_probe_consts[64] = {0.999999, 0.999998, 0.999997, 0.999996};
-template <int CHAINS, int UNIFORM>
-__global__ void fp64_ldc_probe_kernel(int64_t iters, double *sink) {
-    double a[CHAINS];
-#pragma unroll
-    for (int j = 0; j < CHAINS; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
-    const double kc = 1e-6;
-    // UNIFORM = 1: the index follows the loop counter (LDCU, uniform datapath);
-    // UNIFORM = 0: it comes from the chain's own value, like a table lookup (LDC with a per-thread
-    // address)
-    for (int64_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 16 / CHAINS; r++)
-#pragma unroll
-            for (int j = 0; j < CHAINS; j++) {
-                const uint32_t idx = UNIFORM ? (uint32_t) (it + j + r)
-                                             : (uint32_t) __double2loint(a[j]);
-                const double kb = c_probe_consts[idx & 3u];
-                a[j] = fma(a[j], kb, kc);
-            }
-    }
-    double s = 0.;
-#pragma unroll
-    for (int j = 0; j < CHAINS; j++) s += a[j];
-    if (s == 123456.789) sink[0] = s;
-}
-
-// Same with the multiplier read from shared memory (LDS, warp-uniform address = broadcast).
-template <int CHAINS>
-__global__ void fp64_lds_probe_kernel(int64_t iters, double *sink) {
-    __shared__ double s_consts[64];
-    if (threadIdx.x < 64) s_consts[threadIdx.x] = 0.999999 - 1e-6 * (threadIdx.x & 3);
-    __syncthreads();
-    double a[CHAINS];
-#pragma unroll
-    for (int j = 0; j < CHAINS; j++) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
-    const double kc = 1e-6;
-    for (int64_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 16 / CHAINS; r++)
-#pragma unroll
-            for (int j = 0; j < CHAINS; j++) {
-                const double kb = s_consts[(uint32_t) (it + j + r) & 3u];
-                a[j] = fma(a[j], kb, kc);
-            }
-    }
-    double s = 0.;
-#pragma unroll
-    for (int j = 0; j < CHAINS; j++) s += a[j];
-    if (s == 123456.789) sink[0] = s;
-}
-
-// Issue-slot probe: 16 independent DFMA chains interleaved with NINT independent 32-bit integer
-// multiply-adds per DFMA.  If the time per DFMA does not grow with NINT <= 1, non-FP64 instructions
-// issue in the shadow of the half-rate FP64 dispatch; if it grows, they compete for issue cycles.
-template <int NINT>
-__global__ void fp64_mix_probe_kernel(int64_t iters, double *sink) {
-    double a[16];
-    uint32_t x[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
-        x[j] = threadIdx.x * 2654435761u + j;
-    }
-    const double kb = 0.999999, kc = 1e-6;
-    for (int64_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            a[j] = fma(a[j], kb, kc);
-#pragma unroll
-            for (int t = 0; t < NINT; t++)
-                asm volatile("mad.lo.u32 %0, %0, 1664525, 1013904223;" : "+r"(x[j]));
-        }
-    }
-    double s = 0.;
-    uint32_t y = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        s += a[j];
-        y ^= x[j];
-    }
-    if (s == 123456.789 || y == 0x12345678u) sink[0] = s + y;
-}
+namespace noa_b200 {
 
 // ------------------------------------------------------------------------------------------
 // host side of the C ABI
@@ -634,8 +188,6 @@ static int device_info(DeviceInfo &info) {
     return 0;
 }
 
-static int g_max_blocks_per_sm = 0;   // measurement hook (0 = whatever fits)
-
 template <typename Kernel>
 static int persistent_grid(Kernel kernel, int64_t work_items, int &blocks) {
     DeviceInfo info;
@@ -645,7 +197,6 @@ static int persistent_grid(Kernel kernel, int64_t work_items, int &blocks) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (e != cudaSuccess) return (int) e;
     if (per_sm < 1) per_sm = 1;
-    if (g_max_blocks_per_sm > 0 && per_sm > g_max_blocks_per_sm) per_sm = g_max_blocks_per_sm;
     const int64_t need = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t) info.sm_count * per_sm;
     blocks = (int) (need < cap ? need : cap);
@@ -670,9 +221,9 @@ static int launch_vmap(const double *K, const double *q, double *out, int64_t n,
     // one pair per thread so the (large) integrand is instantiated once
     constexpr bool kStreaming = (PROCESS == 0 || PROCESS == 3);
     if (kStreaming && aligned16(K, q, out) && n >= 2) {
-        int rc = persistent_grid(vmap_kernel<PROCESS, 2>, n >> 1, blocks);
+        int rc = persistent_grid(vmap_kernel<PROCESS, NOA_STREAM_VEC>, n / NOA_STREAM_VEC, blocks);
         if (rc) return rc;
-        vmap_kernel<PROCESS, 2><<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
+        vmap_kernel<PROCESS, NOA_STREAM_VEC><<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
     } else {
         int rc = persistent_grid(vmap_kernel<PROCESS, 1>, n, blocks);
         if (rc) return rc;
@@ -681,30 +232,11 @@ static int launch_vmap(const double *K, const double *q, double *out, int64_t n,
     return after_launch();
 }
 
-// How the exchange form runs and where it fences its remote stores:
-//   3 = persistent CTAs pulling rows from a queue, one fence per CTA at the end (default)
-//   0 = one CTA per row, each writer lane fences right after its stores
-//   1 = one CTA per row, one lane fences after the CTA barrier (NCCL's simple-protocol pattern)
-//   2 = one CTA per row, only the last CTA of the grid fences (measurement only: not a sufficient
-//       ordering on its own)
-//   4 = one CTA per row with unfenced remote stores, then a second one-warp kernel that exchanges
-//       the flags (the kernel boundary orders the stores)
-static int g_exchange_fence_mode = 3;
-static int g_pair_mode = 0;   // 0: one pair per thread (default), 1: one node per lane
-
 static int vmap_impl(int process, const double *K, const double *q, double *out, int64_t n,
                      const Params &p, cudaStream_t s) {
     switch (process) {
         case NOA_DCS_BREMSSTRAHLUNG: return launch_vmap<0>(K, q, out, n, p, s);
-        case NOA_DCS_PAIR_PRODUCTION:
-            if (g_pair_mode == 1) {
-                int blocks = 0;
-                int rc = persistent_grid(vmap_pair_lanes_kernel, n * 8, blocks);
-                if (rc) return rc;
-                vmap_pair_lanes_kernel<<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
-                return after_launch();
-            }
-            return launch_vmap<1>(K, q, out, n, p, s);
+        case NOA_DCS_PAIR_PRODUCTION: return launch_vmap<1>(K, q, out, n, p, s);
         case NOA_DCS_PHOTONUCLEAR: return launch_vmap<2>(K, q, out, n, p, s);
         case NOA_DCS_IONISATION: return launch_vmap<3>(K, q, out, n, p, s);
     }
@@ -720,9 +252,159 @@ static int vmap_all_impl(const double *K, const double *q, double *out, int64_t 
     return after_launch();
 }
 
+// ---- table launches ---------------------------------------------------------------------------
+using TableKernel = void (*)(const double *, int64_t, TableOut, TablePlan, Params);
+
+template <bool PERSISTENT>
+static TableKernel table_kernel_for(unsigned mask) {
+    switch (mask) {
+        case 1u: return table_kernel<1u, PERSISTENT>;
+        case 2u: return table_kernel<2u, PERSISTENT>;
+        case 4u: return table_kernel<4u, PERSISTENT>;
+        case 8u: return table_kernel<8u, PERSISTENT>;
+    }
+    return table_kernel<15u, PERSISTENT>;
+}
+
+static int rows_per_item(int process) {
+    return (process == NOA_DCS_BREMSSTRAHLUNG || process == NOA_DCS_IONISATION)
+                   ? TableCfg<0>::R
+                   : TableCfg<1>::R;
+}
+
+// How a multi-process build is launched: one kernel per process, chained with programmatic
+// dependent launch (each with the register budget its integrand wants), or one combined kernel.
+// Measured on config 4 (profiles/r02_table_variants.jsonl): 10^4 rows per process 4.49 ms split
+// against 4.63 combined, but 1 250 rows per process (one rank of eight) 0.645 split against 0.608
+// combined -- with few waves of rows the boundaries between four kernels cost more than the
+// combined kernel's one-size register budget.  Hence: split from kTableSplitRows rows on.
+// NOA_DCS_TABLE_LAUNCH=split|combined (read once, not a run-time switch) forces one form so both
+// stay measurable.
+constexpr int64_t kTableSplitRows = 4096;
+static bool table_launch_split(int64_t rows) {
+    static const int forced = [] {
+        const char *e = std::getenv("NOA_DCS_TABLE_LAUNCH");
+        if (e && !std::strcmp(e, "combined")) return 0;
+        if (e && !std::strcmp(e, "split")) return 1;
+        return -1;
+    }();
+    if (forced >= 0) return forced == 1;
+    return rows >= kTableSplitRows;
+}
+
+static int launch_table(TableKernel kernel, unsigned grid, bool dependent, cudaStream_t s,
+                        const double *K, int64_t nK, const TableOut &out, const TablePlan &plan,
+                        const Params &p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (dependent) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, K, nK, out, plan, p);
+    if (e != cudaSuccess) return (int) e;
+    return after_launch();
+}
+
+static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
+                      double xlow, int32_t min_points, double A, double I, int32_t Z, double mass,
+                      TableOut out, void *stream) {
+    if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1)
+        return NOA_DCS_EINVAL;
+    cudaStream_t s = (cudaStream_t) stream;
+    const bool exchange = out.flags[0] != nullptr;
+    if (nK == 0 || (!out.del[0] && !out.cel[0])) {
+        if (!exchange) return 0;
+        out.total_ctas = 1;
+        table_signal_kernel<<<1, 32, 0, s>>>(out);
+        return after_launch();
+    }
+    if (!K) return NOA_DCS_EINVAL;
+    if (nK > 0x3fffffffLL) return NOA_DCS_ERANGE;
+    DeviceInfo info;
+    int rc = device_info(info);
+    if (rc) return rc;
+    const Params p = make_params(A, I, Z, mass);
+    if (!single_row && process_mask != 15u) {
+        // rows of processes that were not asked for are zero, not whatever the tables held
+        const int64_t blocks = (nK + 255) / 256;
+        table_zero_rows_kernel<<<(unsigned) (blocks > 1184 ? 1184 : blocks), 256, 0, s>>>(
+                nK, 15u & ~process_mask, out);
+        rc = after_launch();
+        if (rc) return rc;
+    }
+
+    static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
+                                       NOA_DCS_BREMSSTRAHLUNG, NOA_DCS_IONISATION};
+    TablePlan all{};
+    all.cells = ((uint32_t) min_points + 5u) / 6u;
+    all.xlow = xlow;
+    for (int i = 0; i < 4; i++) {
+        const int pr = heavy_first[i];
+        if (!((process_mask >> pr) & 1u)) continue;
+        const int R = rows_per_item(pr);
+        all.process[all.n_slots] = pr;
+        all.out_row[all.n_slots] = single_row ? 0 : pr;
+        all.items[all.n_slots] = (uint32_t) ((nK + R - 1) / R);
+        all.n_slots++;
+    }
+
+    // the launches of this build: one combined kernel, or one per process
+    TablePlan plans[4];
+    TableKernel kernels[4];
+    unsigned grids[4];
+    int n_launch = 0;
+    if (all.n_slots == 1 || !table_launch_split(nK)) {
+        plans[0] = all;
+        const unsigned mask = all.n_slots == 1 ? (1u << all.process[0]) : 15u;
+        kernels[0] = exchange ? table_kernel_for<true>(mask) : table_kernel_for<false>(mask);
+        n_launch = 1;
+    } else {
+        for (int i = 0; i < all.n_slots; i++) {
+            TablePlan one = all;
+            one.n_slots = 1;
+            one.process[0] = all.process[i];
+            one.out_row[0] = all.out_row[i];
+            one.items[0] = all.items[i];
+            one.queue = i;
+            plans[i] = one;
+            const unsigned mask = 1u << all.process[i];
+            kernels[i] = exchange ? table_kernel_for<true>(mask) : table_kernel_for<false>(mask);
+        }
+        n_launch = all.n_slots;
+    }
+    uint32_t total_ctas = 0;
+    for (int i = 0; i < n_launch; i++) {
+        uint64_t items = 0;
+        for (int sl = 0; sl < plans[i].n_slots; sl++) items += plans[i].items[sl];
+        if (exchange) {
+            int per_sm = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[i],
+                                                                          kThreads, 0);
+            if (e != cudaSuccess) return (int) e;
+            const uint64_t cap = (uint64_t) info.sm_count * (per_sm < 1 ? 1 : per_sm);
+            if (items > cap) items = cap;
+        }
+        grids[i] = (unsigned) items;
+        total_ctas += grids[i];
+    }
+    out.total_ctas = total_ctas;
+    for (int i = 0; i < n_launch; i++) {
+        rc = launch_table(kernels[i], grids[i], i > 0, s, K, nK, out, plans[i], p);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 }  // namespace noa_b200
 
 #include "coulomb_kernels.cuh"
+#include "material_kernels.cuh"
 
 using namespace noa_b200;
 
@@ -744,8 +426,12 @@ const char *noa_dcs_strerror(int code) {
         case NOA_DCS_EINVAL: return "noa_dcs: invalid argument";
         case NOA_DCS_ERANGE: return "noa_dcs: size out of range";
         case NOA_DCS_ENODEV: return "noa_dcs: no CUDA device (this library has no CPU path)";
+        case NOA_DCS_ENONCCL: return "noa_dcs: NCCL is not loaded in this process";
+        case NOA_DCS_ELIBM: return "noa_dcs: the host libm differs from the one the kernels restate "
+                                   "(results would not be bit-identical to the reference)";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t) code);
+    if (code <= NOA_DCS_ENCCL_BASE) return "noa_dcs: NCCL error (code = NOA_DCS_ENCCL_BASE - ncclResult_t)";
     return "noa_dcs: unknown error";
 }
 
@@ -770,25 +456,6 @@ int noa_dcs_div_recomputes(int64_t *count, int reset) {
     }
     if (e != cudaSuccess) return (int) e;
     if (count) *count = (int64_t) v;
-    return 0;
-}
-
-// test/bench hook: 0 = pair per thread, 1 = node per lane.  Not part of the reference surface.
-int noa_dcs_set_pair_mode(int mode) {
-    if (mode != 0 && mode != 1) return NOA_DCS_EINVAL;
-    g_pair_mode = mode;
-    return 0;
-}
-
-int noa_dcs_set_max_blocks_per_sm(int blocks) {
-    if (blocks < 0) return NOA_DCS_EINVAL;
-    g_max_blocks_per_sm = blocks;
-    return 0;
-}
-
-int noa_dcs_set_exchange_fence_mode(int mode) {
-    if (mode < 0 || mode > 4) return NOA_DCS_EINVAL;
-    g_exchange_fence_mode = mode;
     return 0;
 }
 
@@ -835,49 +502,6 @@ int noa_dcs_vmap_mixture_f64(unsigned process_mask, const double *K, const doubl
     return 0;
 }
 
-static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
-                      double xlow, int32_t min_points, double A, double I, int32_t Z, double mass,
-                      const TableOut &out, void *stream) {
-    if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1)
-        return NOA_DCS_EINVAL;
-    if (nK == 0 || (!out.del[0] && !out.cel[0])) {
-        if (!out.flags[0]) return 0;
-        table_signal_kernel<<<1, 32, 0, (cudaStream_t) stream>>>(out);
-        return after_launch();
-    }
-    if (!K) return NOA_DCS_EINVAL;
-    TablePlan plan{};
-    for (int i = 0; i < 4; i++) plan.out_row[i] = single_row ? 0 : i;
-    static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
-                                       NOA_DCS_BREMSSTRAHLUNG, NOA_DCS_IONISATION};
-    for (int i = 0; i < 4; i++)
-        if ((process_mask >> heavy_first[i]) & 1u) plan.process[plan.n_slots++] = heavy_first[i];
-    plan.cells = ((uint32_t) min_points + 5u) / 6u;
-    plan.xlow = xlow;
-    const int64_t blocks = nK * plan.n_slots;
-    if (blocks > 0x7fffffffLL) return NOA_DCS_ERANGE;
-    DeviceInfo info;
-    int rc = device_info(info);
-    if (rc) return rc;
-    const Params p = make_params(A, I, Z, mass);
-    if (out.flags[0] != nullptr && out.fence_mode == 3) {
-        int grid = 0;
-        rc = persistent_grid(table_exchange_kernel, blocks * kThreads, grid);
-        if (rc) return rc;
-        table_exchange_kernel<<<grid, kThreads, 0, (cudaStream_t) stream>>>(K, nK, out, plan, p);
-        return after_launch();
-    }
-    table_kernel<<<(unsigned) blocks, kThreads, 0, (cudaStream_t) stream>>>(K, nK, out, plan, p);
-    if (out.flags[0] != nullptr && out.fence_mode == 4) {
-        // the kernel boundary makes the rows visible system-wide; a one-warp kernel then does
-        // the flag exchange
-        rc = after_launch();
-        if (rc) return rc;
-        table_signal_kernel<<<1, 32, 0, (cudaStream_t) stream>>>(out);
-    }
-    return after_launch();
-}
-
 static TableOut local_out(double *del, double *cel, int64_t nK) {
     TableOut out{};
     out.n_peers = 1;
@@ -906,15 +530,12 @@ int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t n
     if (nK == 0) return 0;
     if (!K || !scratch || !table) return NOA_DCS_EINVAL;
     const int64_t columns = 8 * nK;
-    // rows of processes outside the mask must mix to 0, not to whatever the scratch held
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t) n_elements * columns * sizeof(double),
-                                    (cudaStream_t) stream);
-    if (e != cudaSuccess) return (int) e;
     MixWeights m{};
     m.n_elements = n_elements;
     for (int el = 0; el < n_elements; el++) {
         m.w[el] = w[el];
         double *part = scratch + (int64_t) el * columns;
+        // rows of processes outside the mask are zeroed by the build itself
         int rc = table_impl(process_mask, false, K, nK, xlow, min_points, A[el], I[el], Z[el], mass,
                             local_out(part, part + 4 * nK, nK), stream);
         if (rc) return rc;
@@ -952,23 +573,24 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
                                double xlow, int32_t min_points, double A, double I, int32_t Z,
                                double mass, int32_t n_peers, int32_t my_peer,
                                double *const *peer_del, double *const *peer_cel,
-                               uint32_t *const *peer_flags, uint32_t *done, uint32_t epoch,
+                               uint32_t *const *peer_flags, uint32_t *sync, uint32_t epoch,
                                int64_t n_total, int64_t first_row, int64_t row_stride,
-                               void *stream) {
+                               double timeout_seconds, void *stream) {
     if (n_peers < 1 || n_peers > NOA_DCS_MAX_PEERS || my_peer < 0 || my_peer >= n_peers)
         return NOA_DCS_EINVAL;
-    if (!peer_del || !peer_cel || !peer_flags || !done) return NOA_DCS_EINVAL;
+    if (!peer_del || !peer_cel || !peer_flags || !sync) return NOA_DCS_EINVAL;
     if (n_total < 0 || first_row < 0 || row_stride < 1 || n_local < 0) return NOA_DCS_EINVAL;
     if (n_local > 0 && first_row + (n_local - 1) * row_stride >= n_total) return NOA_DCS_ERANGE;
+    if (!(timeout_seconds > 0.)) timeout_seconds = NOA_DCS_DEFAULT_EXCHANGE_TIMEOUT_S;
     TableOut out{};
     out.n_peers = n_peers;
     out.me = my_peer;
     out.n_total = n_total;
     out.first_row = first_row;
     out.row_stride = row_stride;
-    out.done = done;
+    out.sync = sync;
     out.epoch = epoch;
-    out.fence_mode = g_exchange_fence_mode;
+    out.timeout_ns = (uint64_t) (timeout_seconds * 1e9);
     for (int j = 0; j < n_peers; j++) {
         if (!peer_del[j] || !peer_cel[j] || !peer_flags[j]) return NOA_DCS_EINVAL;
         out.del[j] = peer_del[j];
@@ -989,6 +611,32 @@ int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, doubl
                       local_out(integrand == 0 ? result : nullptr,
                                 integrand == 1 ? result : nullptr, n),
                       stream);
+}
+
+// ncclAllGather through the NCCL the process already has (torch's bundled one, or the system's):
+// resolved at first use so this library carries no link-time NCCL dependency.
+int noa_dcs_allgather_f64(double *table, int64_t count_per_rank, int32_t rank, void *nccl_comm,
+                          void *stream) {
+    if (!table || count_per_rank < 0 || rank < 0 || !nccl_comm) return NOA_DCS_EINVAL;
+    if (count_per_rank == 0) return 0;
+    typedef int (*AllGatherFn)(const void *, void *, size_t, int, void *, cudaStream_t);
+    static AllGatherFn fn = [] {
+        void *sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+        if (!sym) {
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (h) sym = dlsym(h, "ncclAllGather");
+        }
+        return (AllGatherFn) sym;
+    }();
+    if (!fn) return NOA_DCS_ENONCCL;
+    const int nccl_float64 = 8;   // ncclDouble (nccl.h: ncclFloat64 = 8)
+    // in place: rank r's slice sits at table + r * count_per_rank
+    const int rc = fn(table + (int64_t) rank * count_per_rank, table, (size_t) count_per_rank,
+                      nccl_float64, nccl_comm, (cudaStream_t) stream);
+    if (rc != 0) return NOA_DCS_ENCCL_BASE - rc;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
 }
 
 int noa_dcs_stager_create(noa_dcs_stager **out, int64_t chunk_pairs, int32_t n_slots) {
@@ -1079,14 +727,17 @@ int noa_dcs_vmap_host_f64(noa_dcs_stager *st, int process, const double *h_K, co
     return rc;
 }
 
-// 1 if `ptr` is page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)
-static bool device_addressable_host(const void *ptr) {
+// Device-side address of page-locked host memory the device can reach (cudaHostAlloc /
+// cudaHostRegister); nullptr for anything else.  For registered memory the device address need not
+// equal the host address, so the kernel is always given this one.
+static void *device_address_of_host(const void *ptr) {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
         (void) cudaGetLastError();
-        return false;
+        return nullptr;
     }
-    return attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+    if (attr.type != cudaMemoryTypeHost) return nullptr;
+    return attr.devicePointer;
 }
 
 int noa_dcs_vmap_pinned_f64(int process, const double *h_K, const double *h_q, double *h_result,
@@ -1094,50 +745,66 @@ int noa_dcs_vmap_pinned_f64(int process, const double *h_K, const double *h_q, d
     if (process < 0 || process >= NOA_DCS_NPROCESS || n < 0) return NOA_DCS_EINVAL;
     if (n == 0) return 0;
     if (!h_K || !h_q || !h_result) return NOA_DCS_EINVAL;
-    if (!device_addressable_host(h_K) || !device_addressable_host(h_q) ||
-        !device_addressable_host(h_result))
-        return NOA_DCS_EINVAL;
+    const double *d_K = (const double *) device_address_of_host(h_K);
+    const double *d_q = (const double *) device_address_of_host(h_q);
+    double *d_result = (double *) device_address_of_host(h_result);
+    if (!d_K || !d_q || !d_result) return NOA_DCS_EINVAL;
     // The element-wise kernels run unchanged on the mapped host addresses: their coalesced loads
     // and stores cross PCIe themselves and overlap with the arithmetic of the other resident
     // warps.  Measured alternatives (TMA bulk-copy ring with mbarriers; per-thread cp.async
     // prefetch into shared memory) were slower or equal -- profiles/r01_host_path_variants.md.
     const Params p = make_params(A, I, Z, mass);
-    return vmap_impl(process, h_K, h_q, h_result, n, p, (cudaStream_t) stream);
+    return vmap_impl(process, d_K, d_q, d_result, n, p, (cudaStream_t) stream);
 }
 
-int noa_dcs_fp64_probe(int64_t iters, int32_t blocks, int32_t threads, double *sink,
-                       void *stream) {
-    if (iters < 1 || blocks < 1 || threads < 1 || threads > 1024 || !sink) return NOA_DCS_EINVAL;
-    fp64_probe_kernel<0><<<blocks, threads, 0, (cudaStream_t) stream>>>(iters, sink);
-    return after_launch();
-}
 
-int noa_dcs_fp64_probe_mode(int32_t mode, int64_t iters, int32_t blocks, int32_t threads,
-                            double *sink, void *stream) {
-    if (iters < 1 || blocks < 1 || threads < 1 || threads > 1024 || !sink) return NOA_DCS_EINVAL;
-    cudaStream_t s = (cudaStream_t) stream;
-    switch (mode) {
-        case 0: fp64_probe_kernel<0><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 1: fp64_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 2: fp64_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 3: fp64_probe_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 4: fp64_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 5: fp64_mix_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 6: fp64_mix_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 7: fp64_mix_probe_kernel<3><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 20: fp64_ldc_probe_kernel<1, 1><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 21: fp64_ldc_probe_kernel<1, 0><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 22: fp64_ldc_probe_kernel<4, 1><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 23: fp64_ldc_probe_kernel<4, 0><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 24: fp64_lds_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 25: fp64_lds_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 10: fp64_chain_probe_kernel<1><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 11: fp64_chain_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 12: fp64_chain_probe_kernel<4><<<blocks, threads, 0, s>>>(iters, sink); break;
-        case 13: fp64_chain_probe_kernel<8><<<blocks, threads, 0, s>>>(iters, sink); break;
-        default: return NOA_DCS_EINVAL;
+// ---- host libm self-check ---------------------------------------------------------------------
+// Bit-exactness against the reference's CPU path rests on the host libm being the one the device
+// routines restate (glibc >= 2.28, FMA variant): make_params() evaluates pow / log / exp on the
+// host exactly as the reference does, and the kernels' exp / log / log10 reproduce that libm.  On a
+// different libm the results would silently be "a few ulp" off, which the pair-production
+// integrand amplifies to ~1e-10.  This check compares the host's exp / log / log10 with the host
+// build of glibm.cuh (same tables as the device) on 3 x 1024 arguments and pow with known answers.
+static const glibm::Tables h_selfcheck_tables = {GLIBM_EXP_TABLE_INIT, GLIBM_LOG_TABLE_INIT};
+
+int noa_dcs_selfcheck(int64_t *mismatches) {
+    const glibm::Tab T = glibm::make_host_tab(&h_selfcheck_tables);
+    int64_t bad = 0;
+    uint64_t state = 0x9E3779B97F4A7C15ULL;
+    auto next = [&state]() {          // splitmix64
+        uint64_t z = (state += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    };
+    auto same = [](double a, double b) { return glibm::to_bits(a) == glibm::to_bits(b); };
+    for (int i = 0; i < 1024; i++) {
+        const double u = (double) (next() >> 11) * 0x1p-53;            // [0, 1)
+        const double v = (double) (next() >> 11) * 0x1p-53;
+        const double xe = (u - 0.5) * 80.;                             // exp: |x| < 40
+        const double xl = std::ldexp(0.5 + 0.5 * v, (int) (u * 80.) - 40);   // log: 2^-41 .. 2^40
+        const double xn = 0.93 + 0.14 * v;                             // log near one
+        if (!same(std::exp(xe), glibm::exp_any(xe, T))) bad++;
+        if (!same(std::log(xl), glibm::log_any(xl, T))) bad++;
+        if (!same(std::log(xn), glibm::log_any(xn, T))) bad++;
+        if (!same(std::log10(xl), glibm::log10(xl, T))) bad++;
     }
-    return after_launch();
+    static const struct {
+        double a, b;
+        uint64_t bits;
+    } pow_kat[] = {
+        {11.0, 1. / 3., 0x4001cab612df9a45ULL},     {11.0, -1. / 3., 0x3fdcc6f8f0d0ed76ULL},
+        {11.0, -2. / 3., 0x3fc9e108d5a254c3ULL},    {22.0, 0.27, 0x40026e48b2ce2eadULL},
+        {82.0, 1. / 3., 0x401160bfc12dd090ULL},     {207.2, 0.27, 0x4010e266ff9d65c5ULL},
+        {8.0, -2. / 3., 0x3fd0000000000000ULL},     {15.999, 0.27, 0x4000e9790b7a4a0aULL},
+        {26.0, -1. / 3., 0x3fd59a78b28f888bULL},    {55.845, 0.27, 0x4007b39532d0b74eULL},
+    };
+    for (const auto &c : pow_kat) {
+        volatile double a = c.a, b = c.b;       // keep the call (no constant folding)
+        if (glibm::to_bits(std::pow(a, b)) != c.bits) bad++;
+    }
+    if (mismatches) *mismatches = bad;
+    return bad == 0 ? 0 : NOA_DCS_ELIBM;
 }
 
 int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t *sm_count) {
@@ -1146,10 +813,10 @@ int noa_dcs_launch_info(int process, int32_t *blocks, int32_t *threads, int32_t 
     if (rc) return rc;
     int b = 0;
     switch (process) {
-        case 0: rc = persistent_grid(vmap_kernel<0, 2>, INT64_MAX / 2, b); break;
+        case 0: rc = persistent_grid(vmap_kernel<0, NOA_STREAM_VEC>, INT64_MAX / 2, b); break;
         case 1: rc = persistent_grid(vmap_kernel<1, 1>, INT64_MAX / 2, b); break;
         case 2: rc = persistent_grid(vmap_kernel<2, 1>, INT64_MAX / 2, b); break;
-        case 3: rc = persistent_grid(vmap_kernel<3, 2>, INT64_MAX / 2, b); break;
+        case 3: rc = persistent_grid(vmap_kernel<3, NOA_STREAM_VEC>, INT64_MAX / 2, b); break;
         case 4: rc = persistent_grid(vmap_all_kernel, INT64_MAX / 2, b); break;
         default: return NOA_DCS_EINVAL;
     }

@@ -2,7 +2,7 @@
 // docs/pms/muon_dcs.cu:8-16 (`bremsstrahlung` on CUDA) and docs/pms/muon_dcs.cc:8-45 (the four
 // processes + `serialise`), all on the GPU: standard rock, muon, GIL released during the call.
 // It goes through the LibTorch boundary (torch_api.cc), i.e. exactly what a C++ user links.
-#include "../../include/noa_b200/pms_dcs_cuda.hh"
+#include "../../include/noa_b200/pms_dcs.hh"
 
 #include <torch/extension.h>
 
@@ -80,6 +80,72 @@ inline torch::Tensor soft_scattering(torch::Tensor kinetic_energies) {
     return result;
 }
 
+// The reference's CPU call sites, spelled exactly as in test/unit/test-dcs-calc.cc:22-131 and
+// docs/pms/muon_dcs.cc:8-27 (include/noa_b200/pms_dcs.hh makes them compile unchanged); `K`, `q` are
+// CPU (or CUDA) tensors.  Returns {the four dcs::vmap results, the eight vmap_integral columns at
+// 180 points, dcs::map / pmap / pvmap of pair production}.
+inline std::vector<torch::Tensor> reference_call_sites(torch::Tensor kinetic_energies,
+                                                       torch::Tensor recoil_energies) {
+    std::vector<torch::Tensor> out;
+    {
+        const auto result = torch::zeros_like(kinetic_energies);
+        dcs::vmap(dcs::bremsstrahlung)(result, kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                       MUON_MASS);
+        out.push_back(result);
+    }
+    {
+        const auto result = torch::zeros_like(kinetic_energies);
+        dcs::vmap(dcs::pair_production)(
+                result,
+                kinetic_energies,
+                recoil_energies,
+                STANDARD_ROCK, MUON_MASS);
+        out.push_back(result);
+    }
+    {
+        const auto result = torch::zeros_like(kinetic_energies);
+        dcs::vmap(dcs::photonuclear)(result, kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                     MUON_MASS);
+        out.push_back(result);
+    }
+    {
+        const auto result = torch::zeros_like(kinetic_energies);
+        dcs::vmap(dcs::ionisation)(result, kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                   MUON_MASS);
+        out.push_back(result);
+    }
+#define NOA_B200_COLUMN(F, G)                                                                     \
+    {                                                                                             \
+        const auto result = torch::zeros_like(kinetic_energies);                                  \
+        dcs::vmap_integral(                                                                       \
+                dcs::recoil_integral(dcs::F, dcs::G))(                                            \
+                result,                                                                           \
+                kinetic_energies,                                                                 \
+                dcs::X_FRACTION, STANDARD_ROCK, MUON_MASS, 180);                                  \
+        out.push_back(result);                                                                    \
+    }
+    NOA_B200_COLUMN(bremsstrahlung, del_integrand)
+    NOA_B200_COLUMN(bremsstrahlung, cel_integrand)
+    NOA_B200_COLUMN(pair_production, del_integrand)
+    NOA_B200_COLUMN(pair_production, cel_integrand)
+    NOA_B200_COLUMN(photonuclear, del_integrand)
+    NOA_B200_COLUMN(photonuclear, cel_integrand)
+    NOA_B200_COLUMN(ionisation, del_integrand)
+    NOA_B200_COLUMN(ionisation, cel_integrand)
+#undef NOA_B200_COLUMN
+    out.push_back(dcs::map(dcs::pair_production)(kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                                 MUON_MASS));
+    out.push_back(dcs::pmap(dcs::pair_production)(kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                                  MUON_MASS));
+    {
+        const auto result = torch::zeros_like(kinetic_energies);
+        dcs::pvmap(dcs::pair_production)(result, kinetic_energies, recoil_energies, STANDARD_ROCK,
+                                         MUON_MASS);
+        out.push_back(result);
+    }
+    return out;
+}
+
 inline void serialise(torch::Tensor tensor, std::string path) { torch::save(tensor, path); }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -104,5 +170,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           "coulomb_data + coulomb_transport(mu) + hard_scattering for standard rock");
     m.def("soft_scattering", &soft_scattering, py::call_guard<py::gil_scoped_release>(),
           "Soft-scattering transverse transport for standard rock");
+    m.def("reference_call_sites", &reference_call_sites, py::call_guard<py::gil_scoped_release>(),
+          "The reference's CPU call expressions (dcs::vmap(dcs::f)(...), vmap_integral(...)) on "
+          "CPU or CUDA tensors");
     m.def("serialise", &serialise, py::call_guard<py::gil_scoped_release>(), "Save tensor to disk");
 }

@@ -1,0 +1,389 @@
+// Energy-loss tables: dcs::vmap_integral(dcs::recoil_integral(f, del|cel_integrand))
+// (src/noa/pms/dcs.hh:89-130, 955-1001; src/noa/utils/numerics.hh:72-108), every (process, energy)
+// row of the DEL / CEL tables from one DCS evaluation per node.
+//
+// Work item = R rows of one process, handled by one CTA:
+//   * the nodes of the composite 6-point rule are spread over the 256 threads; every thread writes
+//     its two node terms (f q h w, f q q h w) into shared memory;
+//   * the terms are then added strictly in node order (numerics.hh:84-87: `res += f(x) h w[j]`), one
+//     lane per (row, integrand) chain, the 2R chains in adjacent lanes of warp 0 (one DADD per step
+//     for all of them).  A chain is 1002 dependent additions = 4.4 us whatever else happens, so
+//     - the two cheap processes (bremsstrahlung, ionisation: a row evaluates in less time than it
+//       takes to add up) put R = 4 rows into a pass and quarter that cost per row (config 4,
+//       bremsstrahlung rows: 0.257 / 0.204 / 0.181 ms at R = 1 / 2 / 4);
+//     - terms that are exactly zero are skipped: x + (+-0) = x for every x a chain can hold (it
+//       starts at +0 and +0 + -0 = +0), so only the index range that holds non-zero terms is
+//       walked -- rows below a process's kinematic threshold cost no summation at all.
+//   * lanes 0 .. 2R-1 finish with acc / (K + mass) and store the value into the local table and,
+//     in the multi-GPU forms, into every peer's table over NVLink.
+// Items are ordered heavy first (photonuclear, pair production, bremsstrahlung, ionisation; energy
+// descending inside a process) so the end of the schedule is made of cheap rows.
+//
+// The row body is instantiated per process (`table_item<PROCESS>`, out of line): every integrand
+// gets its own register allocation instead of one 64-register body that holds all four (636 B of
+// spills, 145 MB of local-memory traffic per build in round 1).  Two launch shapes use it:
+//   table_kernel<MASK, false>   one CTA per item (grid = number of items)
+//   table_kernel<MASK, true>    persistent CTAs popping items from a device-side queue; used by
+//                               the multi-GPU exchange, where each CTA pays ONE system-scope fence
+// MASK = 15 is the combined kernel (all processes, register budget of the largest); single-bit
+// masks are per-process kernels with their own launch bounds, chained with programmatic dependent
+// launch so the tail of one process overlaps the head of the next.
+#pragma once
+
+#include <climits>
+
+#include "dcs_device.cuh"
+
+namespace noa_b200 {
+
+constexpr int kTableTerms = 1536;   // node terms staged per pass and integrand: 2 x 12 KB
+#ifndef NOA_TABLE_LIGHT_ROWS
+#define NOA_TABLE_LIGHT_ROWS 4
+#endif
+constexpr int kTableMaxRows = 4;
+
+template <int PROCESS>
+struct TableCfg {
+    static constexpr int R = (PROCESS == 0 || PROCESS == 3) ? NOA_TABLE_LIGHT_ROWS : 1;
+};
+
+// Where the finished rows go: `n_peers` destination tables (this GPU's own and, in the multi-GPU
+// build, every peer's, mapped over NVLink), each [4][n_total]; local row r is global row
+// first_row + r * row_stride.
+struct TableOut {
+    int32_t n_peers;
+    int32_t me;               // index of this GPU among the peers (exchange form only)
+    int64_t n_total;
+    int64_t first_row;
+    int64_t row_stride;
+    double *del[NOA_DCS_MAX_PEERS];
+    double *cel[NOA_DCS_MAX_PEERS];
+    // exchange form (noa_dcs_table_exchange_f64): flags[j] = peer j's array of n_peers epoch words;
+    // sync = this GPU's words {CTA counter, timeouts, -, -, queue 0..3}; flags[0] == nullptr otherwise
+    uint32_t *flags[NOA_DCS_MAX_PEERS];
+    uint32_t *sync;
+    uint32_t epoch;
+    uint32_t total_ctas;      // CTAs of all launches of this build (the last one to finish signals)
+    uint64_t timeout_ns;      // how long to wait for a peer before giving up (trap)
+};
+
+struct TablePlan {
+    int32_t n_slots;          // processes in this launch
+    int32_t process[4];       // heaviest first
+    int32_t out_row[4];       // output row of process p (p for full tables, 0 for a single column)
+    uint32_t items[4];        // items of slot s = ceil(nK / R(process))
+    uint32_t cells;           // ceil(min_points / 6)
+    int32_t queue;            // persistent form: index of this launch's queue word (sync[4 + queue])
+    double xlow;
+};
+
+struct TableShared {
+    StagedShared staged;
+    double2 gl6[6];                         // {node, weight} of the 6-point rule
+    double terms[2 * kTableTerms];          // [node][chain], chain = 2 row + integrand
+    double row_k[kTableMaxRows], row_lb[kTableMaxRows], row_h[kTableMaxRows];
+    int64_t row_at[kTableMaxRows];          // destination index of the row, -1 = no such row
+    int32_t row_quad[kTableMaxRows];        // 1 = quadrature, 0 = closed form / no row
+    int32_t lo, hi;                         // index range of the non-zero terms of the pass
+    uint32_t next[2];                       // persistent form: the CTA's next item
+};
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+__device__ __forceinline__ void pdl_release_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// no-op unless the launch carried the programmatic-serialisation attribute; then: the previous
+// kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void pdl_wait_prerequisites() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Tail of the exchange form.  Every CTA has stored its values (local + peers) and fenced them at
+// system scope; the last CTA of the build to get here publishes this GPU's epoch into every peer's
+// flag array (release, system scope) and then waits until every peer's epoch has arrived in its own
+// -- so when the last kernel of the build retires, the complete table is in this GPU's memory.  No
+// host round trip, no separate barrier kernel.  A peer that does not show up within
+// `timeout_ns` (wall clock) is fatal: the timeout counter is bumped and the kernel traps, so the
+// launch fails instead of handing back a partial table.
+__device__ __forceinline__ void table_exchange_tail(const TableOut &out) {
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    const uint32_t arrived = atomicAdd(out.sync, 1u);
+    if (arrived != out.total_ctas - 1) return;
+    // re-armed for the next build on this stream
+    out.sync[0] = 0;
+#pragma unroll
+    for (int w = 4; w < 8; w++) out.sync[w] = 0;
+    __threadfence_system();
+    for (int j = 0; j < out.n_peers; j++)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(out.flags[j] + out.me),
+                     "r"(out.epoch)
+                     : "memory");
+    const uint64_t t0 = global_timer_ns();
+    for (int j = 0; j < out.n_peers; j++) {
+        const uint32_t *slot = out.flags[out.me] + j;
+        for (;;) {
+            uint32_t seen;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(slot) : "memory");
+            if ((int32_t) (seen - out.epoch) >= 0) break;
+            if (global_timer_ns() - t0 > out.timeout_ns) {
+                atomicAdd(out.sync + 1, 1u);
+                __threadfence_system();
+                __trap();
+            }
+            __nanosleep(100);
+        }
+    }
+}
+
+// Measured alternative (NOA_TABLE_EVAL_CALL=1): the two quadrature-bound integrands called, not
+// inlined, from the row body so that they get the register budget to themselves.  It loses 2.7 %
+// (config 4: 4.494 against 4.380 ms, profiles/r02_table_variants.jsonl) -- the caller-saved state
+// around the call costs more than the spills it avoids -- so the integrand stays inline.
+#ifndef NOA_TABLE_EVAL_CALL
+#define NOA_TABLE_EVAL_CALL 0
+#endif
+template <int PROCESS>
+__device__ __noinline__ double dcs_value_call(double K, double q, const Params &p,
+                                              const glibm::Tab &T) {
+    return dcs_value<PROCESS, true>(K, q, p, T);
+}
+
+// One item: rows nK-1 - (item R + r), r = 0 .. R-1, of `PROCESS` (descending energy).  Called by
+// every thread of the CTA with the shared buffers free to overwrite.
+template <int PROCESS>
+__device__ __noinline__ void table_item(uint32_t item, int slot, const double *__restrict__ K,
+                                        int64_t nK, const TableOut &out, const TablePlan &plan,
+                                        const Params &p, const glibm::Tab &T, TableShared &s,
+                                        uint32_t *queue, uint32_t *s_next) {
+    constexpr int R = TableCfg<PROCESS>::R;
+    constexpr int CH = 2 * R;
+    static_assert(R <= kTableMaxRows && kTableTerms % R == 0, "rows per pass");
+    const int tid = threadIdx.x;
+
+    if (tid < R) {
+        const int64_t row = nK - 1 - ((int64_t) item * R + tid);
+        int quad = 0;
+        int64_t at = -1;
+        if (row >= 0) {
+            const double k = K[row];
+            at = (int64_t) plan.out_row[slot] * out.n_total + out.first_row + row * out.row_stride;
+            s.row_k[tid] = k;
+            quad = !(PROCESS == 3 && k <= p.i_kthr);          // dcs.hh:963-966, 987-990
+            if (quad) {
+                const double lb = glibm::log(k * plan.xlow, T);
+                const double ub = glibm::log(k, T);
+                s.row_lb[tid] = lb;
+                s.row_h[tid] = (ub - lb) / plan.cells;
+            }
+        }
+        s.row_at[tid] = at;
+        s.row_quad[tid] = quad;
+    }
+    if (tid == 0) {
+        s.lo = INT_MAX;
+        s.hi = -1;
+    }
+    __syncthreads();
+
+    bool any_quad = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) any_quad |= (s.row_quad[r] != 0);
+
+    // chain owned by this lane (tid < CH): row tid / 2, integrand tid % 2 (0 DEL, 1 CEL)
+    const int my_row = (tid < CH) ? (tid >> 1) : 0;
+    const bool my_quad = (tid < CH) && s.row_quad[my_row] != 0;
+    double acc = 0.;
+
+    if (any_quad) {
+        const uint32_t total = plan.cells * 6u;
+        constexpr uint32_t per_pass = kTableTerms / R;
+        for (uint32_t base = 0; base < total; base += per_pass) {
+            const uint32_t count = min(per_pass, total - base);
+            int lo = INT_MAX, hi = -1;
+            for (uint32_t e = tid; e < R * count; e += kThreads) {
+                uint32_t r = 0, il = e;
+                if (R > 1) {
+#pragma unroll
+                    for (int t = 1; t < R; t++)
+                        if (il >= count) {
+                            il -= count;
+                            r++;
+                        }
+                }
+                if (!s.row_quad[r]) continue;
+                const uint32_t i = base + il;
+                const uint32_t cell = i / 6u;
+                const uint32_t j = i - cell * 6u;
+                const double h = s.row_h[r];
+                const double k = s.row_k[r];
+                const double2 xw = s.gl6[j];
+                const double x = s.row_lb[r] + h * (cell + xw.x);
+                const double q = glibm::exp(x, T);
+                const double f = (NOA_TABLE_EVAL_CALL && (PROCESS == 1 || PROCESS == 2))
+                                         ? dcs_value_call<PROCESS>(k, q, p, T)
+                                         : dcs_value<PROCESS, true>(k, q, p, T);
+                const double w = xw.y;
+                const double fq = f * q;
+                const double td = fq * h * w;           // del_integrand, dcs.hh:107-109
+                const double tc = fq * q * h * w;       // cel_integrand, dcs.hh:111-113
+                s.terms[il * CH + 2 * r] = td;
+                s.terms[il * CH + 2 * r + 1] = tc;
+                if (td != 0. || tc != 0.) {             // NaN counts as non-zero
+                    lo = min(lo, (int) il);
+                    hi = max(hi, (int) il);
+                }
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if ((tid & 31) == 0 && hi >= 0) {
+                atomicMin(&s.lo, lo);
+                atomicMax(&s.hi, hi);
+            }
+            __syncthreads();
+            // res += term, strictly in node order (numerics.hh:84-87), one lane per chain
+            if (tid < 32) {
+                const int first = s.lo, last = s.hi;
+                if (my_quad)
+                    for (int il = first; il <= last; il++) acc += s.terms[il * CH + tid];
+                __syncwarp();
+                if (tid == 0) {
+                    s.lo = INT_MAX;
+                    s.hi = -1;
+                }
+            } else if (tid == 64 && queue != nullptr && base + per_pass >= total) {
+                // persistent form: this idle lane pops the CTA's next item while the chains run --
+                // late enough that a heavy row in flight never sits on an item another CTA could
+                // have started, early enough that the atomic's round trip is hidden
+                *s_next = atomicAdd(queue, 1u);
+            }
+            __syncthreads();
+        }
+    } else if (queue != nullptr && tid == 64) {
+        *s_next = atomicAdd(queue, 1u);
+    }
+
+    if (tid < CH && s.row_at[my_row] >= 0) {
+        const int integrand = tid & 1;
+        double *const *dst = integrand ? out.cel : out.del;
+        if (dst[0] != nullptr) {
+            const double k = s.row_k[my_row];
+            const double v = my_quad ? acc / (k + p.mass)
+                                     : ionisation_closed_form(k, plan.xlow, integrand, p, T);
+            const int64_t at = s.row_at[my_row];
+            // one store per destination: the local table and, over NVLink, each peer's copy
+            for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
+        }
+    }
+}
+
+template <unsigned MASK>
+struct TableMinBlocks {
+    static constexpr int value = (MASK == 2u)   ? NOA_MINB_TABLE_PAIR
+                                 : (MASK == 4u) ? NOA_MINB_TABLE_PHOTO
+                                 : (MASK == 15u) ? NOA_MINB_TABLE_ALL
+                                                 : NOA_MINB_TABLE_LIGHT;
+};
+
+template <unsigned MASK>
+__device__ __forceinline__ void table_dispatch(uint32_t b, const double *__restrict__ K, int64_t nK,
+                                               const TableOut &out, const TablePlan &plan,
+                                               const Params &p, const glibm::Tab &T, TableShared &s,
+                                               uint32_t *queue, uint32_t *s_next) {
+    int slot = 0;
+    while (slot < plan.n_slots - 1 && b >= plan.items[slot]) b -= plan.items[slot++];
+    switch (plan.process[slot]) {      // CTA-uniform
+        case 0:
+            if (MASK & 1u) table_item<0>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            break;
+        case 1:
+            if (MASK & 2u) table_item<1>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            break;
+        case 2:
+            if (MASK & 4u) table_item<2>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            break;
+        default:
+            if (MASK & 8u) table_item<3>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            break;
+    }
+}
+
+template <unsigned MASK, bool PERSISTENT>
+__global__ void __launch_bounds__(kThreads, TableMinBlocks<MASK>::value)
+table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
+             const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
+    __shared__ TableShared s;
+    if (threadIdx.x < 6) {
+        s.gl6[threadIdx.x] = make_double2(c_gl6_x[threadIdx.x], c_gl6_w[threadIdx.x]);
+    }
+    const glibm::Tab T = stage_all(s.staged, p);
+    // the next launch of the build (another process: disjoint rows) may start filling SMs as
+    // soon as every CTA of this one is resident or done
+    pdl_release_dependents();
+    if (PERSISTENT) {
+        uint32_t total = 0;
+        for (int i = 0; i < plan.n_slots; i++) total += plan.items[i];
+        uint32_t *queue = out.sync + 4 + plan.queue;
+        if (threadIdx.x == 64) s.next[0] = atomicAdd(queue, 1u);
+        for (int cur = 0;; cur ^= 1) {
+            __syncthreads();                   // s.next[cur] written; shared buffers free again
+            const uint32_t b = s.next[cur];
+            if (b >= total) break;
+            table_dispatch<MASK>(b, K, nK, out, plan, p, T, s, queue, &s.next[cur ^ 1]);
+        }
+    } else {
+        table_dispatch<MASK>(blockIdx.x, K, nK, out, plan, p, T, s, nullptr, nullptr);
+        // scatter form without flags: the writer lanes fence their own remote stores
+        if (out.n_peers > 1 && out.flags[0] == nullptr && threadIdx.x < 32) __threadfence_system();
+    }
+    // completion order along the chain: this kernel does not retire before its predecessor has
+    if (threadIdx.x == 0) pdl_wait_prerequisites();
+    if (out.flags[0] != nullptr) table_exchange_tail(out);
+}
+
+// Rows of processes outside the mask are defined to be zero in every destination table.
+__global__ void table_zero_rows_kernel(int64_t n_local, unsigned zero_mask,
+                                       const __grid_constant__ TableOut out) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < n_local; r += stride)
+        for (int pr = 0; pr < 4; pr++) {
+            if (!((zero_mask >> pr) & 1u)) continue;
+            const int64_t at = (int64_t) pr * out.n_total + out.first_row + r * out.row_stride;
+            for (int j = 0; j < out.n_peers; j++) {
+                if (out.del[j]) out.del[j][at] = 0.;
+                if (out.cel[j]) out.cel[j][at] = 0.;
+            }
+        }
+}
+
+// Material tables: out[c] = sum_e parts[e][c] * w[e], e in composition order, starting from 0
+// (the per-element mixing of src/noa/3rdparty/_pumas/pumas.c:8054-8078).
+struct MixWeights {
+    int32_t n_elements;
+    double w[NOA_DCS_MAX_ELEMENTS];
+};
+
+__global__ void mix_tables_kernel(const double *__restrict__ parts, double *__restrict__ out,
+                                  int64_t columns, const __grid_constant__ MixWeights m) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < columns; c += stride) {
+        double acc = 0.;
+        for (int e = 0; e < m.n_elements; e++) acc += parts[(int64_t) e * columns + c] * m.w[e];
+        out[c] = acc;
+    }
+}
+
+// A rank with no rows of its own still has to take part in the exchange.
+__global__ void table_signal_kernel(const __grid_constant__ TableOut out) {
+    if (threadIdx.x == 0) pdl_wait_prerequisites();
+    table_exchange_tail(out);
+}
+
+}  // namespace noa_b200

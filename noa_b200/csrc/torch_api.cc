@@ -1,28 +1,95 @@
 // LibTorch boundary: defines noa::pms::dcs::cuda::* (include/noa_b200/pms_dcs_cuda.hh) on top of
-// the C ABI (include/noa_dcs_b200.h).  Compiled by the host compiler only -- no nvcc, no kernels
+// the C ABI (include/noa_dcs_b200.h).  CUDA tensors are passed straight through (asynchronous on
+// the current stream); CPU tensors -- the reference's CPU call sites, dcs::vmap(f)(result, K, q,
+// ...) on host memory (src/noa/pms/dcs.hh:35-60, test/unit/test-dcs-calc.cc:44-48) -- run on the
+// GPU through the host-buffer entry points and are complete on return, like the CPU path they
+// replace: pinned tensors are read and written in place by the kernel
+// (noa_dcs_vmap_pinned_f64), pageable ones go through the chunked copy pipeline
+// (noa_dcs_vmap_host_f64).  There is still no CPU implementation.  Compiled by the host compiler only -- no nvcc, no kernels
 // here -- so it builds in about a minute despite <torch/...> (the reference's dcs.cuh TU needs
 // ~5 min under nvcc).
 #include "../../include/noa_b200/pms_dcs_cuda.hh"
 #include "../../include/noa_dcs_b200.h"
 
+#include <c10/cuda/CUDAFunctions.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/torch.h>
 
+#include <mutex>
+
 namespace noa::pms::dcs::cuda {
 
     namespace {
-        void check_tensor(const torch::Tensor &t, const char *name) {
+        void check_layout(const torch::Tensor &t, const char *name) {
             TORCH_CHECK(t.defined(), name, " is undefined");
-            TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor (this build has no CPU path)");
+            TORCH_CHECK(t.is_cuda() || t.is_cpu(), name, " must be a CUDA or a CPU tensor");
             TORCH_CHECK(t.scalar_type() == torch::kFloat64, name, " must be float64, got ",
                         t.scalar_type());
             TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
         }
 
+        void check_tensor(const torch::Tensor &t, const char *name) {
+            check_layout(t, name);
+            TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+        }
+
+        bool pinned(const torch::Tensor &t) {
+            try {
+                return t.is_pinned();
+            } catch (const c10::Error &) {      // no CUDA hooks in this process
+                return false;
+            }
+        }
+
+        // device scratch + streams of the pageable host path, created on first use per device
+        struct HostStager {
+            std::mutex mu;
+            noa_dcs_stager *stager = nullptr;
+            int device = -1;
+            ~HostStager() {
+                if (stager) noa_dcs_stager_destroy(stager);
+            }
+        };
+        HostStager &host_stager() {
+            static HostStager s;
+            return s;
+        }
+
+        // dcs::vmap(f)(result, K, q, element, mass) on CPU tensors; process 4 = all four
+        void host_vmap(int process, const torch::Tensor &result, const torch::Tensor &K,
+                       const torch::Tensor &q, const AtomicElement &el, const ParticleMass &mass) {
+            const int64_t n = K.numel();
+            if (n == 0) return;
+            if (process < NOA_DCS_NPROCESS && pinned(K) && pinned(q) && pinned(result)) {
+                const auto stream = c10::cuda::getCurrentCUDAStream();
+                const int rc = noa_dcs_vmap_pinned_f64(process, K.data_ptr<double>(),
+                                                       q.data_ptr<double>(),
+                                                       result.data_ptr<double>(), n, el.A, el.I,
+                                                       el.Z, mass, (void *) stream.stream());
+                TORCH_CHECK(rc == 0, "noa_dcs_vmap_pinned_f64 failed: ", noa_dcs_strerror(rc));
+                stream.synchronize();
+                return;
+            }
+            auto &hs = host_stager();
+            const std::lock_guard<std::mutex> lock(hs.mu);
+            const int device = (int) c10::cuda::current_device();
+            if (hs.stager == nullptr || hs.device != device) {
+                if (hs.stager) noa_dcs_stager_destroy(hs.stager);
+                hs.stager = nullptr;
+                const int rc = noa_dcs_stager_create(&hs.stager, int64_t(1) << 18, 3);
+                TORCH_CHECK(rc == 0, "noa_dcs_stager_create failed: ", noa_dcs_strerror(rc));
+                hs.device = device;
+            }
+            const int rc = noa_dcs_vmap_host_f64(hs.stager, process, K.data_ptr<double>(),
+                                                 q.data_ptr<double>(), result.data_ptr<double>(),
+                                                 n, el.A, el.I, el.Z, mass);
+            TORCH_CHECK(rc == 0, "noa_dcs_vmap_host_f64 failed: ", noa_dcs_strerror(rc));
+        }
+
         void check_pair(const torch::Tensor &K, const torch::Tensor &q) {
-            check_tensor(K, "kinetic_energies");
-            check_tensor(q, "recoil_energies");
+            check_layout(K, "kinetic_energies");
+            check_layout(q, "recoil_energies");
             TORCH_CHECK(K.numel() == q.numel(), "kinetic_energies and recoil_energies differ in "
                         "size: ", K.numel(), " vs ", q.numel());
             TORCH_CHECK(K.device() == q.device(), "tensors are on different devices");
@@ -36,38 +103,46 @@ namespace noa::pms::dcs::cuda {
             return (void *) c10::cuda::getCurrentCUDAStream(t.device().index()).stream();
         }
 
-        void vmap_process(int process, const Calculation &result, const Energies &K,
-                          const Energies &q, const AtomicElement &el, const ParticleMass &mass) {
+    }  // namespace
+
+    void vmap_dcs(int process, const Calculation &result, const Energies &K, const Energies &q,
+                  const AtomicElement &el, const ParticleMass &mass) {
+        {
+            TORCH_CHECK(process >= 0 && process < NOA_DCS_NPROCESS, "process must be 0..3");
             check_pair(K, q);
-            check_tensor(result, "result");
+            check_layout(result, "result");
             TORCH_CHECK(result.numel() == K.numel(), "result has ", result.numel(),
                         " elements, expected ", K.numel());
             TORCH_CHECK(result.device() == K.device(), "result is on a different device");
+            if (!K.is_cuda()) {
+                host_vmap(process, result, K, q, el, mass);
+                return;
+            }
             const c10::cuda::CUDAGuard guard(K.device());
             check_rc(noa_dcs_vmap_f64(process, K.data_ptr<double>(), q.data_ptr<double>(),
                                       result.data_ptr<double>(), K.numel(), el.A, el.I, el.Z, mass,
                                       current_stream(K)),
                      "noa_dcs_vmap_f64");
         }
+    }
 
-        Calculation map_process(int process, const Energies &K, const Energies &q,
-                                const AtomicElement &el, const ParticleMass &mass) {
-            // the reference allocates zeros_like (dcs.cuh:48); every element is overwritten
-            const auto result = torch::empty_like(K);
-            vmap_process(process, result, K, q, el, mass);
-            return result;
-        }
-    }  // namespace
+    Calculation map_dcs(int process, const Energies &K, const Energies &q, const AtomicElement &el,
+                        const ParticleMass &mass) {
+        // the reference allocates zeros_like (dcs.cuh:48, dcs.hh:57); every element is overwritten
+        const auto result = torch::empty_like(K);
+        vmap_dcs(process, result, K, q, el, mass);
+        return result;
+    }
 
 #define NOA_B200_DEFINE_PROCESS(NAME, ID)                                                        \
     void vmap_##NAME(const Calculation &result, const Energies &kinetic_energies,                \
                      const Energies &recoil_energies, const AtomicElement &element,              \
                      const ParticleMass &mass) {                                                 \
-        vmap_process(ID, result, kinetic_energies, recoil_energies, element, mass);              \
+        vmap_dcs(ID, result, kinetic_energies, recoil_energies, element, mass);              \
     }                                                                                            \
     Calculation map_##NAME(const Energies &kinetic_energies, const Energies &recoil_energies,    \
                            const AtomicElement &element, const ParticleMass &mass) {             \
-        return map_process(ID, kinetic_energies, recoil_energies, element, mass);                \
+        return map_dcs(ID, kinetic_energies, recoil_energies, element, mass);                \
     }
 
     NOA_B200_DEFINE_PROCESS(bremsstrahlung, NOA_DCS_BREMSSTRAHLUNG)
@@ -79,9 +154,14 @@ namespace noa::pms::dcs::cuda {
     void vmap_all(const Calculation &result, const Energies &K, const Energies &q,
                   const AtomicElement &el, const ParticleMass &mass) {
         check_pair(K, q);
-        check_tensor(result, "result");
+        check_layout(result, "result");
         TORCH_CHECK(result.numel() == 4 * K.numel(), "result must hold 4 x ", K.numel(),
                     " elements");
+        TORCH_CHECK(result.device() == K.device(), "result is on a different device");
+        if (!K.is_cuda()) {
+            host_vmap(NOA_DCS_NPROCESS, result, K, q, el, mass);
+            return;
+        }
         const c10::cuda::CUDAGuard guard(K.device());
         check_rc(noa_dcs_vmap_all_f64(K.data_ptr<double>(), q.data_ptr<double>(),
                                       result.data_ptr<double>(), K.numel(), el.A, el.I, el.Z, mass,
@@ -102,6 +182,9 @@ namespace noa::pms::dcs::cuda {
                              const std::vector<AtomicElement> &elements,
                              const std::vector<Scalar> &mass_fractions, const ParticleMass &mass) {
         check_pair(K, q);
+        if (!K.is_cuda())       // host tensors: evaluate on the device, hand back a host tensor
+            return map_material(K.to(torch::kCUDA), q.to(torch::kCUDA), elements, mass_fractions,
+                                mass).to(torch::kCPU);
         TORCH_CHECK(!elements.empty() && elements.size() == mass_fractions.size() &&
                     elements.size() <= NOA_DCS_MAX_ELEMENTS,
                     "a material has 1..", NOA_DCS_MAX_ELEMENTS, " elements with one mass fraction "
@@ -128,10 +211,21 @@ namespace noa::pms::dcs::cuda {
     void vmap_integral(int process, int integrand, const Calculation &result, const Energies &K,
                        const EnergyTransfer &xlow, const AtomicElement &el,
                        const ParticleMass &mass, const Index min_points) {
-        check_tensor(K, "kinetic_energies");
-        check_tensor(result, "result");
+        check_layout(K, "kinetic_energies");
+        check_layout(result, "result");
         TORCH_CHECK(result.numel() == K.numel(), "result has ", result.numel(),
                     " elements, expected ", K.numel());
+        TORCH_CHECK(result.device() == K.device(), "result is on a different device");
+        if (!K.is_cuda()) {
+            // dcs::vmap_integral on CPU tensors (test/unit/test-dcs-calc.cc:22-42): the energies go
+            // to the device, the column comes back into `result` (blocking copy)
+            if (K.numel() == 0) return;
+            const auto Kd = K.to(torch::kCUDA);
+            const auto rd = torch::empty_like(Kd);
+            vmap_integral(process, integrand, rd, Kd, xlow, el, mass, min_points);
+            result.copy_(rd.view_as(result));
+            return;
+        }
         const c10::cuda::CUDAGuard guard(K.device());
         check_rc(noa_dcs_vmap_integral_f64(process, integrand, K.data_ptr<double>(),
                                            result.data_ptr<double>(), K.numel(), xlow, min_points,
@@ -159,7 +253,8 @@ namespace noa::pms::dcs::cuda {
 
     Calculation tables(const Energies &K, const EnergyTransfer &xlow, const AtomicElement &el,
                        const ParticleMass &mass, const Index min_points) {
-        check_tensor(K, "kinetic_energies");
+        check_layout(K, "kinetic_energies");
+        if (!K.is_cuda()) return tables(K.to(torch::kCUDA), xlow, el, mass, min_points).to(torch::kCPU);
         const auto result = torch::zeros({2, 4, K.numel()}, K.options());
         if (K.numel() == 0) return result;
         const c10::cuda::CUDAGuard guard(K.device());

@@ -453,6 +453,13 @@ class HostStager:
         if out is None:
             out = torch.empty(shape, dtype=torch.float64,
                               pin_memory=kinetic_energies.is_pinned())
+        else:
+            # the C ABI writes n (or 4 n) doubles through the raw pointer: refuse anything else
+            expected = (4 if dcs_func is None else 1) * n
+            if (not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != torch.float64
+                    or not out.is_contiguous() or out.numel() != expected):
+                raise ValueError(f"out must be a contiguous float64 CPU tensor of {expected} "
+                                 "elements")
         A, I, Z = _element(element)
         if (dcs_func is not None and self.zero_copy and kinetic_energies.is_pinned()
                 and recoil_energies.is_pinned() and out.is_pinned() and out.is_contiguous()):

@@ -82,7 +82,33 @@ def cyclic_rows(n, rank, world):
     return torch.arange(rank, max(n, rank), world)
 
 
-class TableBuilder:
+class _HostTables:
+    """Host-buffer form shared by the two builders (the e2e path: host K in -> host table out)."""
+
+    def build_host(self, K_host, out_host, xlow, element, mass, min_points, processes=None):
+        """`K_host`: the FULL energy grid [n_K] on the host (pinned for an asynchronous copy);
+        `out_host`: [2, 4, n_K] host tensor that receives the complete table.  Copies the grid to
+        the device, takes this rank's cyclic share, builds + exchanges, copies the table back and
+        synchronises the stream.  Every rank ends with the full table on its host."""
+        if K_host.is_cuda or out_host.is_cuda or K_host.dtype != torch.float64 \
+                or out_host.dtype != torch.float64:
+            raise ValueError("build_host expects float64 CPU tensors")
+        if K_host.numel() != self.n or out_host.numel() != 8 * self.n \
+                or not K_host.is_contiguous() or not out_host.is_contiguous():
+            raise ValueError(f"build_host expects contiguous K [{self.n}] and out [2, 4, {self.n}]")
+        dev = self.K_local.device
+        if getattr(self, "K_full", None) is None:
+            self.K_full = torch.empty(self.n, dtype=torch.float64, device=dev)
+        self.K_full.copy_(K_host.reshape(-1), non_blocking=True)
+        if self.n_local:
+            self.K_local.copy_(self.K_full[self.rank::self.world])
+        table = self.build(xlow, element, mass, min_points, processes)
+        out_host.view(2, 4, self.n).copy_(table, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host
+
+
+class TableBuilder(_HostTables):
     """Builds the DEL/CEL tables of one element for all energies `K` across `world` ranks.
 
     `compute(K_local, xlow, element, mass, min_points, out=(del, cel))` defaults to the CUDA table
@@ -100,8 +126,9 @@ class TableBuilder:
         dev, L = K.device, self.rows_per_rank
         # local slice padded to L rows so every rank contributes the same byte count
         self.local = torch.zeros((2, 4, L), dtype=torch.float64, device=dev)
-        self.compact = (torch.zeros((4, self.n_local), dtype=torch.float64, device=dev),
-                        torch.zeros((4, self.n_local), dtype=torch.float64, device=dev))
+        # [DEL | CEL] of the local rows in one buffer: a single GPU hands it out as the table
+        self.compact_buf = torch.zeros((2, 4, self.n_local), dtype=torch.float64, device=dev)
+        self.compact = (self.compact_buf[0], self.compact_buf[1])
         self.gathered = torch.zeros((world, 2, 4, L), dtype=torch.float64, device=dev) \
             if world > 1 else None
         if compute is None:
@@ -115,7 +142,7 @@ class TableBuilder:
         if self.n_local:
             self.compute(self.K_local, xlow, element, mass, min_points, out=self.compact, **kw)
         if self.world == 1:
-            return torch.stack(self.compact)
+            return self.compact_buf      # valid until the next build()
         self.local[0, :, :self.n_local] = self.compact[0]
         self.local[1, :, :self.n_local] = self.compact[1]
         dist.all_gather_into_tensor(self.gathered.view(-1), self.local.view(-1), group=self.group)
@@ -124,7 +151,7 @@ class TableBuilder:
         return full[:, :, :self.n].contiguous()
 
 
-class PeerTableBuilder:
+class PeerTableBuilder(_HostTables):
     """Table build fused with its exchange AND the rank barrier: ONE kernel launch per rank computes
     the rank's cyclic share of the rows, stores every finished value straight into the
     [2, 4, n_K] table of EVERY rank -- its own and, over NVLink, each peer's (buffers from torch
@@ -140,13 +167,20 @@ class PeerTableBuilder:
     `fused_barrier=False` keeps the older two-step form (noa_dcs_table_scatter_f64 followed by a
     symmetric-memory barrier kernel) for comparison.
 
+    A peer that does not arrive within `timeout_s` of wall-clock time is fatal: the kernel bumps
+    the timeout counter and traps, so the next synchronisation on this device raises a CUDA error
+    instead of `build()` having handed back a partial table (`timeouts()` reads the counter where
+    the context survived).  Rows of processes outside a masked build are zero in every rank's table.
+
     Needs an NCCL process group + peer access between the GPUs of the box; `make_table_builder`
-    falls back to the all-gather `TableBuilder` when symmetric memory cannot be set up.
+    falls back to the all-gather `TableBuilder` when symmetric memory cannot be set up on EVERY
+    rank (the ranks agree on the outcome collectively).
     """
 
     FLAG_WORDS = 16     # NOA_DCS_MAX_PEERS 32-bit epoch slots
 
-    def __init__(self, K, rank, world, group=None, fused_barrier=True):
+    def __init__(self, K, rank, world, group=None, fused_barrier=True, timeout_s=30.0,
+                 arm=True):
         import ctypes
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
@@ -156,6 +190,7 @@ class PeerTableBuilder:
         self.n = K.numel()
         self.rank, self.world = rank, world
         self.fused_barrier = fused_barrier
+        self.timeout_s = float(timeout_s)
         rows = cyclic_rows(self.n, rank, world).to(K.device)
         self.n_local = rows.numel()
         self.K_local = K.reshape(-1)[rows].contiguous()
@@ -175,10 +210,18 @@ class PeerTableBuilder:
         self._del = [(vp * world)(*[p + b * per_table * 8 for p in ptrs]) for b in range(2)]
         self._cel = [(vp * world)(*[p + b * per_table * 8 + half for p in ptrs]) for b in range(2)]
         self._flags = (vp * world)(*[p + 2 * per_table * 8 for p in ptrs])
-        self.done = torch.zeros(4, dtype=torch.int32, device=K.device)
+        # {CTA counter, timeouts, 2 reserved, 4 row queues} (noa_dcs_table_exchange_f64: `sync`)
+        self.done = torch.zeros(8, dtype=torch.int32, device=K.device)
         self.epoch = 0
         torch.cuda.synchronize(K.device)
-        self.handle.barrier(channel=0)     # everyone's buffer is zeroed before anyone writes
+        if arm:
+            self.arm()
+
+    def arm(self):
+        """Collective: everyone's buffer is zeroed before anyone writes.  `make_table_builder`
+        defers it until all ranks have agreed that construction succeeded everywhere."""
+        self.handle.barrier(channel=0)
+        return self
 
     def build(self, xlow, element, mass, min_points, processes=None):
         """Returns the full table [2, 4, n_K]; complete, in stream order, when the launch retires."""
@@ -199,7 +242,7 @@ class PeerTableBuilder:
                     mask, c.c_void_p(self.K_local.data_ptr()), self.n_local, float(xlow),
                     int(min_points), float(A), float(I), int(Z), float(mass), self.world, self.rank,
                     self._del[b], self._cel[b], self._flags, c.c_void_p(self.done.data_ptr()),
-                    self.epoch, self.n, self.rank, self.world, stream))
+                    self.epoch, self.n, self.rank, self.world, self.timeout_s, stream))
             else:
                 # peers must be done reading this table before anyone overwrites it
                 self.handle.barrier(channel=0)
@@ -217,12 +260,23 @@ class PeerTableBuilder:
         return int(self.done[1].item())
 
 
-def make_table_builder(K, rank=0, world=1, group=None, prefer_peer=True):
-    """PeerTableBuilder when `world` > 1 and symmetric memory works, else TableBuilder."""
+def make_table_builder(K, rank=0, world=1, group=None, prefer_peer=True, timeout_s=30.0):
+    """PeerTableBuilder when `world` > 1 and symmetric memory works on every rank, else
+    TableBuilder.  The decision is collective: each rank tries to set the peer form up (nothing in
+    that attempt waits for another rank once the symmetric-memory rendezvous itself has returned),
+    the ranks all-reduce(MIN) a success flag, and only a unanimous success arms the peer builders --
+    so the ranks never end up running different exchange protocols."""
     if world > 1 and prefer_peer and K.is_cuda:
+        builder, error = None, None
         try:
-            return PeerTableBuilder(K, rank, world, group)
+            builder = PeerTableBuilder(K, rank, world, group, timeout_s=timeout_s, arm=False)
         except Exception as exc:   # no peer access / symmetric memory unavailable
-            import warnings
-            warnings.warn(f"peer-memory table build unavailable ({exc!r}); using NCCL all-gather")
+            error = exc
+        ok = torch.tensor([1 if builder is not None else 0], dtype=torch.int32, device=K.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            return builder.arm()
+        import warnings
+        warnings.warn("peer-memory table build unavailable on at least one rank "
+                      f"(this rank: {error!r}); every rank uses the NCCL all-gather")
     return TableBuilder(K, rank, world, group=group)

@@ -8,8 +8,8 @@ import pytest
 from conftest import ROOT
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "noa_dcs_b200.h")).read()
+def _declared_symbols(header="noa_dcs_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(noa_dcs_[a-z0-9_]+)\s*\(", text)))
 
@@ -22,8 +22,28 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/noa_dcs_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in noa_b200/_lib.py"
-    assert lib.noa_dcs_abi_version() == 1
+    assert lib.noa_dcs_abi_version() == 2
     assert b"invalid" in lib.noa_dcs_strerror(-1)
+    # measurement hooks are not part of the product library any more
+    for name in ("noa_dcs_set_pair_mode", "noa_dcs_set_exchange_fence_mode",
+                 "noa_dcs_set_max_blocks_per_sm", "noa_dcs_fp64_probe"):
+        assert not hasattr(lib, name), f"{name} must live in libnoa_dcs_b200_probe.so"
+    probe = _lib.load_probe()
+    for name in _declared_symbols("noa_dcs_b200_probe.h"):
+        assert hasattr(probe, name), f"{name} declared in noa_dcs_b200_probe.h but not exported"
+        assert name in _lib.PROBE_SIGNATURES, name
+
+
+def test_host_libm_selfcheck():
+    """noa_dcs_selfcheck: the host's exp / log / log10 / pow are the ones the kernels restate (it
+    also runs at load time; this asserts the count explicitly)."""
+    import ctypes
+    from noa_b200 import _lib
+    lib = _lib.load()
+    bad = ctypes.c_int64(-1)
+    assert lib.noa_dcs_selfcheck(ctypes.byref(bad)) == 0
+    assert bad.value == 0
+    assert b"libm" in lib.noa_dcs_strerror(-5)
 
 
 def test_no_cpu_fallback_without_a_device():

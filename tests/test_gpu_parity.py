@@ -192,16 +192,21 @@ def test_reference_cuda_surface(golden):
 
 
 def test_pair_lane_mapping_gives_identical_results(port):
+    """The node-per-lane mapping of pair production (measurement library, include/
+    noa_dcs_b200_probe.h) against the product's pair-per-thread kernel."""
+    import ctypes
     from noa_b200 import _lib
-    lib = _lib.load()
+    probe = _lib.load_probe()
     K, q = grids.set_a(50000)
     Kd, qd = dev(K), dev(q)
     a = dcs.map(dcs.pair_production)(Kd, qd, ELEMENTS["Pb"], MUON_MASS)
-    try:
-        assert lib.noa_dcs_set_pair_mode(1) == 0
-        b = dcs.map(dcs.pair_production)(Kd, qd, ELEMENTS["Pb"], MUON_MASS)
-    finally:
-        lib.noa_dcs_set_pair_mode(0)
+    b = torch.empty_like(a)
+    A, I, Z = ELEMENTS["Pb"]
+    vp = ctypes.c_void_p
+    _lib.check(probe.noa_dcs_probe_pair_lanes_f64(
+        vp(Kd.data_ptr()), vp(qd.data_ptr()), vp(b.data_ptr()), K.size, A, I, Z, MUON_MASS,
+        vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
     assert torch.equal(a, b)
     assert_parity(b, port.vmap(1, K, q, ELEMENTS["Pb"], MUON_MASS, threads=8), "pair lanes")
 
@@ -276,6 +281,39 @@ def test_material_tables_mix_element_tables(port):
     t2, _ = dcs.cuda.material_tables(dev(K), 0.05, WATER, MUON_MASS, 180,
                                      processes=(dcs.photonuclear,))
     assert torch.equal(t2[:, 2], table[:, 2]) and float(t2[:, [0, 1, 3]].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("n_rows", [1, 2, 3, 255, 1001])
+def test_table_row_pairing_and_thresholds(port, n_rows):
+    """The two cheap processes put two rows into one CTA pass; ionisation switches between the
+    closed form and the quadrature at K = 0.5 (m - me)^2 / me = 10.8 GeV: odd row counts, a single
+    row, and a grid that straddles the switch (so that a pass holds one row of each kind), all
+    four processes, both integrands, against the oracle."""
+    K = grids.table_energies(n_rows, 0.9, 1.2) if n_rows > 1 else np.array([10.9])
+    d, c = dcs.cuda.tables(dev(K), 0.05, ELEMENTS["rock"], MUON_MASS, 1000)
+    for pr in dcs.PROCESSES:
+        for ig, got in ((0, d), (1, c)):
+            want = port.vmap_integral(pr.index, ig, K, 0.05, 1000, ELEMENTS["rock"], MUON_MASS,
+                                      threads=8)
+            assert_parity(got[pr.index], want, ("pairing", n_rows, pr.name, ig))
+
+
+def test_table_config4_sample_against_oracle(port):
+    """BASELINE config 4's own grid (10^4 energies, 1e-2 .. 1e6 GeV, 1000 points): the full GPU
+    table, every 20th energy of it against the oracle (bench.py checks all 8 x 10^4 values against
+    the compiled reference on the B200 box)."""
+    K = grids.table_energies(10000)
+    d, c = dcs.cuda.tables(dev(K), 0.05, ELEMENTS["rock"], MUON_MASS, 1000)
+    idx = np.arange(0, K.size, 20)
+    sel = torch.from_numpy(idx).cuda()
+    for pr in dcs.PROCESSES:
+        for ig, got in ((0, d), (1, c)):
+            want = port.vmap_integral(pr.index, ig, K[idx], 0.05, 1000, ELEMENTS["rock"],
+                                      MUON_MASS, threads=16)
+            assert_parity(got[pr.index][sel], want, ("config 4", pr.name, ig))
+    # a second build gives the same bits (no dependence on CTA scheduling)
+    d2, c2 = dcs.cuda.tables(dev(K), 0.05, ELEMENTS["rock"], MUON_MASS, 1000)
+    assert torch.equal(d, d2) and torch.equal(c, c2)
 
 
 def test_table_odd_node_counts(port):
@@ -399,7 +437,46 @@ def test_cpp_libtorch_boundary_via_pybind(golden):
     with pytest.raises(RuntimeError):
         muons.bremsstrahlung(K.float(), q.float())
     with pytest.raises(RuntimeError):
-        muons.bremsstrahlung(K.cpu(), q.cpu())
+        muons.bremsstrahlung(K, q.cpu())                 # tensors on different devices
+
+
+def test_cpp_reference_cpu_call_sites(golden):
+    """The reference's CPU call expressions -- dcs::vmap(dcs::pair_production)(result, K, q, ...),
+    dcs::vmap_integral(dcs::recoil_integral(f, g))(result, K, xlow, ...), dcs::map / pmap / pvmap
+    (test/unit/test-dcs-calc.cc:22-131, docs/pms/muon_dcs.cc:8-27) -- compiled unchanged against
+    include/noa_b200/pms_dcs.hh, on CPU tensors (pageable and pinned) and on CUDA tensors."""
+    from noa_b200 import muons
+    Kn, qn = golden["N_K"], golden["N_q"]
+    Kt = golden["T_K"]
+    variants = {
+        "pageable": (torch.from_numpy(Kn.copy()), torch.from_numpy(qn.copy())),
+        "pinned": (torch.from_numpy(Kn.copy()).pin_memory(), torch.from_numpy(qn.copy()).pin_memory()),
+        "cuda": (dev(Kn), dev(qn)),
+    }
+    for label, (K, q) in variants.items():
+        out = muons.reference_call_sites(K, q)
+        assert len(out) == 15
+        for t in out:
+            assert t.device == K.device, label
+        for i, name in enumerate(PROC):
+            assert_parity(out[i], golden[f"vmap_N_rock_{name}"], (label, "vmap", name))
+        for t in out[12:]:
+            assert_parity(t, golden["vmap_N_rock_pair_production"], (label, "map/pmap/pvmap"))
+    # the integral columns are pinned by the golden table energies
+    for label, K in (("pageable", torch.from_numpy(Kt.copy())), ("cuda", dev(Kt))):
+        out = muons.reference_call_sites(K, K * 0.0505)
+        i = 4
+        for name in PROC:
+            for ig in ("del", "cel"):
+                assert_parity(out[i], golden[f"integral_rock_{name}_{ig}_180"], (label, name, ig))
+                i += 1
+    # CPU tensors in, CPU tensors out for the table builders too
+    t = muons.tables(torch.from_numpy(Kt.copy()), 0.05, 180)
+    assert not t.is_cuda
+    assert_parity(t[0, 2], golden["integral_rock_photonuclear_del_180"], "tables on CPU tensors")
+    allp = muons.all_processes(variants["pageable"][0], variants["pageable"][1])
+    assert not allp.is_cuda
+    assert_parity(allp[3], golden["vmap_N_rock_ionisation"], "all_processes on CPU tensors")
 
 
 def test_reference_benchmark_cases_cli():

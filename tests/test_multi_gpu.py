@@ -63,12 +63,11 @@ def _worker(rank, world, port, n_rows, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_rows", [257, 1000])
-def test_two_rank_table_build(tmp_path, n_rows):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world,n_rows", [(2, 257), (2, 1000), (4, 1000), (8, 257), (8, 1000)])
+def test_multi_rank_table_build(tmp_path, world, n_rows):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     from noa_b200 import dcs, grids
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_rows, str(tmp_path)), nprocs=world, join=True)
     K = torch.from_numpy(grids.table_energies(n_rows)).cuda()
     d, c = dcs.cuda.tables(K, 0.05, ELEMENTS["rock"], MUON_MASS, 180)
@@ -78,6 +77,8 @@ def test_two_rank_table_build(tmp_path, n_rows):
         assert np.array_equal(got["gather"], want), f"all-gather build differs on rank {r}"
         assert np.array_equal(got["peer"], want), f"{got['kind']} build differs on rank {r}"
         assert np.array_equal(got["again"][:, 1], want[:, 1])
+        # rows of the processes a masked build did not ask for are zero on every rank
+        assert not got["again"][:, [0, 2, 3]].any(), f"stale rows after a masked build, rank {r}"
         assert np.array_equal(got["two_step"], want), f"two-step peer build differs on rank {r}"
         assert int(got["timeouts"]) == 0
         for i in range(12):
@@ -85,3 +86,98 @@ def test_two_rank_table_build(tmp_path, n_rows):
             di, ci = dcs.cuda.tables(K, 0.05, el, MUON_MASS, 60 + 6 * (i % 2))
             assert np.array_equal(got["seq"][i], torch.stack((di, ci)).cpu().numpy()), (r, i)
         print("rank", r, "builder:", got["kind"])
+
+
+def test_cpp_two_rank_ipc_example():
+    """examples/two_rank_table_exchange.cc: a plain C++ host (fork + CUDA IPC, no torch, no NCCL)
+    drives noa_dcs_table_exchange_f64 on two GPUs and compares with a single-GPU build."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "noa_b200", "two_rank_table_exchange")
+    if not os.path.exists(exe):
+        pytest.skip("example not built (make -C noa_b200/csrc example)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=180)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("equals the single-GPU build") == 8 and "OK" in r.stdout
+
+
+def _nccl_worker(rank, world, port, n_rows, tmp):
+    """noa_dcs_allgather_f64 with a raw ncclComm_t made through the NCCL torch has loaded."""
+    import ctypes
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from noa_b200 import _lib, dcs, grids
+    lib = _lib.require_device()
+    torch.zeros(1, device="cuda")                       # CUDA context
+    nccl = None
+    for name in ("libnccl.so.2", "libnccl.so"):
+        try:
+            nccl = ctypes.CDLL(name, mode=ctypes.RTLD_GLOBAL)
+            break
+        except OSError:
+            continue
+    if nccl is None:
+        import glob
+        import site
+        for sp in site.getsitepackages():
+            hits = glob.glob(os.path.join(sp, "nvidia", "nccl", "lib", "libnccl.so*"))
+            if hits:
+                nccl = ctypes.CDLL(hits[0], mode=ctypes.RTLD_GLOBAL)
+                break
+    assert nccl is not None, "no NCCL library found"
+    uid = (ctypes.c_byte * 128)()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    box = [bytes(uid)]
+    dist.broadcast_object_list(box, src=0)
+    uid = (ctypes.c_byte * 128).from_buffer_copy(box[0])
+    comm = ctypes.c_void_p()
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_byte * 128)]
+
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId,
+                                      ctypes.c_int]
+    assert nccl.ncclCommInitRank(ctypes.byref(comm), world, UniqueId(uid), rank) == 0
+    K = grids.table_energies(n_rows)
+    L = (n_rows + world - 1) // world
+    K_local = torch.from_numpy(np.ascontiguousarray(K[rank::world])).cuda()
+    gathered = torch.zeros((world, 2, 4, L), dtype=torch.float64, device="cuda")
+    n_local = K_local.numel()
+    d, c = dcs.cuda.tables(K_local, 0.05, ELEMENTS["rock"], MUON_MASS, 180)
+    gathered[rank, 0, :, :n_local] = d
+    gathered[rank, 1, :, :n_local] = c
+    vp = ctypes.c_void_p
+    _lib.check(lib.noa_dcs_allgather_f64(vp(gathered.data_ptr()), 8 * L, rank, comm,
+                                         vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    # gathered[r, c, p, l] is row l * W + r of column (c, p)
+    full = gathered.permute(1, 2, 3, 0).reshape(2, 4, L * world)[:, :, :n_rows].contiguous()
+    np.save(os.path.join(tmp, f"nccl_r{rank}.npy"), full.cpu().numpy())
+    nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_c_abi_nccl_allgather(tmp_path):
+    """noa_dcs_allgather_f64 (the NCCL form of the exchange SURVEY 8(b) sketches) with a raw
+    ncclComm_t: two ranks, cyclic rows, un-permuted table equals the single-GPU build."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from noa_b200 import dcs, grids
+    world, n_rows = 2, 501
+    mp.spawn(_nccl_worker, args=(world, _free_port(), n_rows, str(tmp_path)), nprocs=world,
+             join=True)
+    K = torch.from_numpy(grids.table_energies(n_rows)).cuda()
+    d, c = dcs.cuda.tables(K, 0.05, ELEMENTS["rock"], MUON_MASS, 180)
+    want = torch.stack((d, c)).cpu().numpy()
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"nccl_r{r}.npy"))
+        assert np.array_equal(got, want), f"rank {r}"
