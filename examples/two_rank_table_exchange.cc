@@ -114,7 +114,12 @@ int main() {
     pid_t pids[2];
     for (int rank = 0; rank < 2; rank++) {       // fork before any CUDA call
         pids[rank] = fork();
-        if (pids[rank] == 0) _exit(run_rank(rank, socks[rank]));
+        if (pids[rank] == 0) {
+            const int rc = run_rank(rank, socks[rank]);
+            std::fflush(stdout);
+            std::fflush(stderr);
+            _exit(rc);
+        }
     }
     int failed = 0;
     for (int rank = 0; rank < 2; rank++) {

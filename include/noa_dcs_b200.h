@@ -185,6 +185,44 @@ int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, doubl
                               int32_t Z, double mass, void *stream);
 
 /*
+ * The recoil integral in the shape of PUMAS's compute_dcs_integral
+ * (src/noa/3rdparty/_pumas/pumas.c:10901-10955) over NOA's DCS and NOA's composite 6-point rule:
+ *   result[i] = 1 / (K[i] + mass) * integral over ln q in [ln(K[i] xlow), ln(K[i] xhigh)] of
+ *               dcs(K[i], q) q^(1 + mode)          mode 0 cross-section, 1 energy loss, 2 straggling
+ * Modes 0 / 1 with xhigh = 1 are noa_dcs_vmap_integral_f64 (closed forms included); everything
+ * else is evaluated by quadrature.  xlow > 0, xhigh > xlow.
+ */
+int noa_dcs_vmap_integral_mode_f64(int process, int mode, const double *K, double *result,
+                                   int64_t n, double xlow, double xhigh, int32_t min_points,
+                                   double A, double I, int32_t Z, double mass, void *stream);
+
+/*
+ * Per-material table assembly: the steps PUMAS runs on per-element DCS
+ * integrals when it tabulates a material, over NOA's DCS (the reference has no such driver; the
+ * oracle is oracle/material_oracle.c driving the reference's scalar DCS).  All outputs are device
+ * arrays; A, I, Z, w are HOST arrays of n_elements entries.
+ *   elem       [n_elements][3][4][nK]  per element and process: CSn (cross-section, x in
+ *              [cutoff, 1]), cel (energy loss, same range), stg (straggling, ionisation only, x in
+ *              [1e-6, cutoff])                                  pumas.c:10768-10808
+ *   cs, cel    [4][nK]  mass-fraction mix per process; straggling [nK]; cs_total [nK] the sum over
+ *              processes, regularised below the threshold; csf [n_elements][4][nK] the normalised
+ *              cumulative fractions used to pick (element, process)
+ *                                                               pumas.c:8054-8111, 8130-8131
+ *   kt, it     (one double / one int32 on the device) the first tabulated energy >= row 1 with a
+ *              non-zero total cross-section and its row           pumas.c:10820-10833
+ *   xt         [n_elements][4][nK]  fractional threshold per process, element and energy: 1 below
+ *              row `it`, else doubling from `cutoff` until the DCS is positive followed by a
+ *              bisection to 1 % of the cutoff                     pumas.c:10839-10880
+ * 4 n_elements + 3 launches (+ the chained table launches), all on `stream`.
+ */
+int noa_dcs_material_assembly_f64(const double *K, int64_t nK, double cutoff, int32_t min_points,
+                                  int32_t n_elements, const double *A, const double *I,
+                                  const int32_t *Z, const double *w, double mass, double *elem,
+                                  double *cs, double *cel, double *straggling, double *csf,
+                                  double *cs_total, double *kt, int32_t *it, double *xt,
+                                  void *stream);
+
+/*
  * Coulomb scattering and soft scattering -- the rest of the reference's dcs.hh surface
  * (SURVEY.md 8(f)); same argument meaning and array layouts as the reference's functors, device
  * pointers, FP64, bit-identical results.

@@ -49,6 +49,14 @@ SIGNATURES = {
     "noa_dcs_allgather_f64": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "noa_dcs_vmap_integral_f64": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64, _f64,
                                                  _i32, _f64, _f64, _i32, _f64, _vp]),
+    "noa_dcs_vmap_integral_mode_f64": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64,
+                                                      _f64, _f64, _i32, _f64, _f64, _i32, _f64,
+                                                      _vp]),
+    "noa_dcs_material_assembly_f64": (ctypes.c_int, [_vp, _i64, _f64, _i32, _i32,
+                                                     ctypes.POINTER(_f64), ctypes.POINTER(_f64),
+                                                     ctypes.POINTER(_i32), ctypes.POINTER(_f64),
+                                                     _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                     _vp, _vp]),
     "noa_dcs_coulomb_data_f64": (ctypes.c_int, [_vp, _i64, _f64, _f64, _i32, _f64, _vp, _vp, _vp,
                                                 _vp, _vp]),
     "noa_dcs_coulomb_transport_f64": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),

@@ -188,15 +188,43 @@ static int device_info(DeviceInfo &info) {
     return 0;
 }
 
+// Resident CTAs per SM of a kernel at kThreads threads.  The occupancy query costs a few
+// microseconds -- a quarter of a 10^4-pair call -- so the answer is kept per kernel (all devices of
+// a box are the same part).
+static int blocks_per_sm(const void *kernel, int &per_sm) {
+    static std::mutex mu;
+    static const void *keys[64];
+    static int vals[64];
+    static int count = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int i = 0; i < count; i++)
+            if (keys[i] == kernel) {
+                per_sm = vals[i];
+                return 0;
+            }
+    }
+    int v = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0);
+    if (e != cudaSuccess) return (int) e;
+    if (v < 1) v = 1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (count < 64) {
+        keys[count] = kernel;
+        vals[count++] = v;
+    }
+    per_sm = v;
+    return 0;
+}
+
 template <typename Kernel>
 static int persistent_grid(Kernel kernel, int64_t work_items, int &blocks) {
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-    if (e != cudaSuccess) return (int) e;
-    if (per_sm < 1) per_sm = 1;
+    rc = blocks_per_sm((const void *) kernel, per_sm);
+    if (rc) return rc;
     const int64_t need = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t) info.sm_count * per_sm;
     blocks = (int) (need < cap ? need : cap);
@@ -220,7 +248,13 @@ static int launch_vmap(const double *K, const double *q, double *out, int64_t n,
     // 128-bit loads/stores pay for the two streaming processes; the quadrature-bound ones keep
     // one pair per thread so the (large) integrand is instantiated once
     constexpr bool kStreaming = (PROCESS == 0 || PROCESS == 3);
-    if (kStreaming && aligned16(K, q, out) && n >= 2) {
+    // latency-sized calls (less than one two-pair CTA per SM, e.g. the reference benchmark's 10^4
+    // pairs) spread one pair per thread over twice as many SMs instead
+    DeviceInfo info;
+    int rc0 = device_info(info);
+    if (rc0) return rc0;
+    const bool wide = n >= (int64_t) info.sm_count * kThreads * 2;
+    if (kStreaming && wide && aligned16(K, q, out)) {
         int rc = persistent_grid(vmap_kernel<PROCESS, NOA_STREAM_VEC>, n / NOA_STREAM_VEC, blocks);
         if (rc) return rc;
         vmap_kernel<PROCESS, NOA_STREAM_VEC><<<blocks, kThreads, 0, s>>>(K, q, out, n, p);
@@ -311,9 +345,15 @@ static int launch_table(TableKernel kernel, unsigned grid, bool dependent, cudaS
     return after_launch();
 }
 
+struct TableOptions {
+    double xhigh = 1.;
+    int32_t second_power = 2;
+    bool quadrature_only = false;
+};
+
 static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
                       double xlow, int32_t min_points, double A, double I, int32_t Z, double mass,
-                      TableOut out, void *stream) {
+                      TableOut out, void *stream, const TableOptions &opt = TableOptions()) {
     if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1)
         return NOA_DCS_EINVAL;
     cudaStream_t s = (cudaStream_t) stream;
@@ -344,6 +384,9 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
     TablePlan all{};
     all.cells = ((uint32_t) min_points + 5u) / 6u;
     all.xlow = xlow;
+    all.xhigh = opt.xhigh;
+    all.second_power = opt.second_power;
+    all.quadrature_only = opt.quadrature_only ? 1 : 0;
     for (int i = 0; i < 4; i++) {
         const int pr = heavy_first[i];
         if (!((process_mask >> pr) & 1u)) continue;
@@ -384,10 +427,9 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
         for (int sl = 0; sl < plans[i].n_slots; sl++) items += plans[i].items[sl];
         if (exchange) {
             int per_sm = 0;
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[i],
-                                                                          kThreads, 0);
-            if (e != cudaSuccess) return (int) e;
-            const uint64_t cap = (uint64_t) info.sm_count * (per_sm < 1 ? 1 : per_sm);
+            rc = blocks_per_sm((const void *) kernels[i], per_sm);
+            if (rc) return rc;
+            const uint64_t cap = (uint64_t) info.sm_count * per_sm;
             if (items > cap) items = cap;
         }
         grids[i] = (unsigned) items;
@@ -611,6 +653,71 @@ int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, doubl
                       local_out(integrand == 0 ? result : nullptr,
                                 integrand == 1 ? result : nullptr, n),
                       stream);
+}
+
+int noa_dcs_vmap_integral_mode_f64(int process, int mode, const double *K, double *result,
+                                   int64_t n, double xlow, double xhigh, int32_t min_points,
+                                   double A, double I, int32_t Z, double mass, void *stream) {
+    if (process < 0 || process >= NOA_DCS_NPROCESS || mode < 0 || mode > 2) return NOA_DCS_EINVAL;
+    if (!(xlow > 0.) || !(xhigh > xlow)) return NOA_DCS_EINVAL;
+    if (n > 0 && !result) return NOA_DCS_EINVAL;
+    if (mode <= 1 && xhigh == 1.)      // dcs::recoil_integral proper, closed forms included
+        return noa_dcs_vmap_integral_f64(process, mode, K, result, n, xlow, min_points, A, I, Z,
+                                         mass, stream);
+    TableOptions opt;
+    opt.xhigh = xhigh;
+    opt.second_power = (mode == 2) ? 3 : 2;
+    opt.quadrature_only = true;
+    return table_impl(1u << process, true, K, n, xlow, min_points, A, I, Z, mass,
+                      local_out(mode == 0 ? result : nullptr, mode == 0 ? nullptr : result, n),
+                      stream, opt);
+}
+
+int noa_dcs_material_assembly_f64(const double *K, int64_t nK, double cutoff, int32_t min_points,
+                                  int32_t n_elements, const double *A, const double *I,
+                                  const int32_t *Z, const double *w, double mass, double *elem,
+                                  double *cs, double *cel, double *straggling, double *csf,
+                                  double *cs_total, double *kt, int32_t *it, double *xt,
+                                  void *stream) {
+    if (n_elements < 1 || n_elements > NOA_DCS_MAX_ELEMENTS || !A || !I || !Z || !w)
+        return NOA_DCS_EINVAL;
+    if (nK < 0 || min_points < 1 || !(cutoff > 1E-06) || !(cutoff < 1.)) return NOA_DCS_EINVAL;
+    if (nK == 0) return 0;
+    if (!K || !elem || !cs || !cel || !straggling || !csf || !cs_total || !kt || !it || !xt)
+        return NOA_DCS_EINVAL;
+    cudaStream_t s = (cudaStream_t) stream;
+    const int64_t n4 = 4 * nK;
+    MixWeights mw{};
+    MaterialParams mp{};
+    mw.n_elements = mp.n_elements = n_elements;
+    // step 1 (pumas.c:10786-10805): CSn / cel from the fused table kernels, the ionisation
+    // straggling integral from their generalised form; the other stg rows are zero
+    for (int el = 0; el < n_elements; el++) {
+        mw.w[el] = mp.w[el] = w[el];
+        mp.p[el] = make_params(A[el], I[el], Z[el], mass);
+        double *e = elem + (int64_t) el * 3 * n4;
+        int rc = table_impl(15u, false, K, nK, cutoff, min_points, A[el], I[el], Z[el], mass,
+                            local_out(e, e + n4, nK), s);
+        if (rc) return rc;
+        cudaError_t ce = cudaMemsetAsync(e + 2 * n4, 0, (size_t) n4 * sizeof(double), s);
+        if (ce != cudaSuccess) return (int) ce;
+        rc = noa_dcs_vmap_integral_mode_f64(NOA_DCS_IONISATION, 2, K, e + 2 * n4 + 3 * nK, nK,
+                                            1E-06, cutoff, min_points, A[el], I[el], Z[el], mass,
+                                            stream);
+        if (rc) return rc;
+    }
+    const int64_t blocks = (nK + 127) / 128;
+    material_mix_kernel<<<(unsigned) (blocks > 1184 ? 1184 : blocks), 128, 0, s>>>(
+            elem, nK, n_elements, mw, cs, cel, straggling, csf, cs_total);
+    int rc = after_launch();
+    if (rc) return rc;
+    material_threshold_kernel<<<1, 256, 0, s>>>(K, nK, cs_total, kt, it);
+    rc = after_launch();
+    if (rc) return rc;
+    const int64_t xt_blocks = ((int64_t) n_elements * n4 + 127) / 128;
+    material_xt_kernel<<<(unsigned) (xt_blocks > 4736 ? 4736 : xt_blocks), 128, 0, s>>>(
+            K, nK, cutoff, it, mp, xt);
+    return after_launch();
 }
 
 // ncclAllGather through the NCCL the process already has (torch's bundled one, or the system's):

@@ -75,6 +75,12 @@ struct TablePlan {
     uint32_t cells;           // ceil(min_points / 6)
     int32_t queue;            // persistent form: index of this launch's queue word (sync[4 + queue])
     double xlow;
+    // generalised form (noa_dcs_vmap_integral_mode_f64; PUMAS's compute_dcs_integral shape,
+    // pumas.c:10901-10955): upper bound ln(K xhigh) instead of ln K, the second chain's integrand
+    // dcs q^second_power (2 = cel_integrand, 3 = straggling), no ionisation closed form
+    double xhigh;
+    int32_t second_power;
+    int32_t quadrature_only;
 };
 
 struct TableShared {
@@ -176,10 +182,12 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
             const double k = K[row];
             at = (int64_t) plan.out_row[slot] * out.n_total + out.first_row + row * out.row_stride;
             s.row_k[tid] = k;
-            quad = !(PROCESS == 3 && k <= p.i_kthr);          // dcs.hh:963-966, 987-990
+            // dcs.hh:963-966, 987-990
+            quad = !(PROCESS == 3 && k <= p.i_kthr && !plan.quadrature_only);
             if (quad) {
                 const double lb = glibm::log(k * plan.xlow, T);
-                const double ub = glibm::log(k, T);
+                const double ub = (plan.xhigh == 1.) ? glibm::log(k, T)
+                                                     : glibm::log(k * plan.xhigh, T);
                 s.row_lb[tid] = lb;
                 s.row_h[tid] = (ub - lb) / plan.cells;
             }
@@ -233,7 +241,9 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
                 const double w = xw.y;
                 const double fq = f * q;
                 const double td = fq * h * w;           // del_integrand, dcs.hh:107-109
-                const double tc = fq * q * h * w;       // cel_integrand, dcs.hh:111-113
+                double y = fq * q;                      // cel_integrand, dcs.hh:111-113
+                if (plan.second_power == 3) y *= q;     // straggling, pumas.c:10945-10949
+                const double tc = y * h * w;
                 s.terms[il * CH + 2 * r] = td;
                 s.terms[il * CH + 2 * r + 1] = tc;
                 if (td != 0. || tc != 0.) {             // NaN counts as non-zero

@@ -408,6 +408,52 @@ class _Cuda:
         return table, scratch.view(ne, 2, 4, n)
 
 
+    # -- PUMAS-style table assembly of a material over NOA's DCS
+    @staticmethod
+    def vmap_integral_mode(result, kinetic_energies, process, mode, xlow, xhigh, element, mass,
+                           min_points):
+        """The recoil integral in PUMAS's compute_dcs_integral shape (pumas.c:10901-10955):
+        integrand dcs q^(1 + mode) in ln q over [ln(K xlow), ln(K xhigh)], / (K + mass).
+        mode 0 cross-section, 1 energy loss, 2 straggling."""
+        lib = _lib.require_device()
+        _check_tensor(result, "result")
+        _check_tensor(kinetic_energies, "kinetic_energies")
+        _same(kinetic_energies, result, "kinetic_energies", "result")
+        A, I, Z = _element(element)
+        with torch.cuda.device(kinetic_energies.device):
+            _lib.check(lib.noa_dcs_vmap_integral_mode_f64(
+                process.index, int(mode), _ptr(kinetic_energies), _ptr(result),
+                kinetic_energies.numel(), float(xlow), float(xhigh), int(min_points), A, I, Z,
+                float(mass), _stream(kinetic_energies.device)))
+
+    @staticmethod
+    def material_assembly(kinetic_energies, cutoff, material, mass, min_points=180):
+        """pumas.c:8054-8111, 10768-10808, 10816-10881 over NOA's DCS, all on the GPU.  Returns a
+        dict of device tensors: elem [ne, 3, 4, n] (CSn, cel, stg per element), cs / cel [4, n],
+        straggling [n], csf [ne, 4, n], cs_total [n], kt [1], it [1] (int32), xt [ne, 4, n]."""
+        lib = _lib.require_device()
+        _check_tensor(kinetic_energies, "kinetic_energies")
+        n = kinetic_energies.numel()
+        ne = len(material.elements)
+        dev = kinetic_energies.device
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)  # noqa: E731
+        out = {"elem": z(ne, 3, 4, n), "cs": z(4, n), "cel": z(4, n), "straggling": z(n),
+               "csf": z(ne, 4, n), "cs_total": z(n), "kt": z(1),
+               "it": torch.zeros(1, dtype=torch.int32, device=dev), "xt": z(ne, 4, n)}
+        A = (ctypes.c_double * ne)(*[float(e.A) for e in material.elements])
+        I = (ctypes.c_double * ne)(*[float(e.I) for e in material.elements])
+        Z = (ctypes.c_int32 * ne)(*[int(e.Z) for e in material.elements])
+        w = (ctypes.c_double * ne)(*[float(f) for f in material.fractions])
+        if n:
+            with torch.cuda.device(dev):
+                _lib.check(lib.noa_dcs_material_assembly_f64(
+                    _ptr(kinetic_energies), n, float(cutoff), int(min_points), ne, A, I, Z, w,
+                    float(mass), _ptr(out["elem"]), _ptr(out["cs"]), _ptr(out["cel"]),
+                    _ptr(out["straggling"]), _ptr(out["csf"]), _ptr(out["cs_total"]),
+                    _ptr(out["kt"]), _ptr(out["it"]), _ptr(out["xt"]), _stream(dev)))
+        return out
+
+
 cuda = _Cuda()
 
 

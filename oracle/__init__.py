@@ -7,4 +7,5 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.  noa_b200/ (the product) must never do so.
 """
-from .cpu import Checker, build_port, build_reference, load_port, load_reference  # noqa: F401
+from .cpu import (Checker, build_port, build_reference, integral_scalar, load_port,  # noqa: F401
+                  load_reference, material_assembly)

@@ -142,6 +142,54 @@ class Checker:
         return out
 
 
+def material_assembly(checker, elements, fractions, mass, K, cutoff, min_points, threads=1):
+    """Per-material table assembly (oracle/material_oracle.c: the PUMAS algorithm,
+    pumas.c:8054-8111, 10768-10808, 10816-10881, 10901-10955) driven by `checker`'s DCS: the
+    compiled reference's scalar functions (kind "reference") or the C port's.  Returns a dict of
+    arrays: elem [ne,3,4,n] (CSn, cel, stg), cs [4,n], cel [4,n], straggling [n], csf [ne,4,n],
+    cs_total [n], xt [ne,4,n] and the scalars kt, it, rc."""
+    port = ctypes.CDLL(PORT_SO)
+    pre = "oracle_" if checker.kind == "port" else "noa_ref_"
+    dcs = getattr(checker._lib, pre + "dcs_scalar")
+    integral = getattr(checker._lib, pre + "integral_scalar")
+    K = _f64(K)
+    n, ne = K.size, len(elements)
+    A = np.array([e[0] for e in elements], dtype=np.float64)
+    I = np.array([e[1] for e in elements], dtype=np.float64)
+    Z = np.array([e[2] for e in elements], dtype=np.int32)
+    w = np.array(fractions, dtype=np.float64)
+    out = {"elem": np.zeros((ne, 3, 4, n)), "cs": np.zeros((4, n)), "cel": np.zeros((4, n)),
+           "straggling": np.zeros(n), "csf": np.zeros((ne, 4, n)), "cs_total": np.zeros(n),
+           "xt": np.zeros((ne, 4, n))}
+    kt, it = ctypes.c_double(0.), ctypes.c_int32(0)
+    fn = port.oracle_material_assembly
+    fn.restype = ctypes.c_int
+    vp = ctypes.c_void_p
+    fn.argtypes = [ctypes.c_int32, _dp, _dp, ctypes.POINTER(ctypes.c_int32), _dp, ctypes.c_double,
+                   _dp, ctypes.c_int64, ctypes.c_double, ctypes.c_int32, vp, vp, _dp, _dp, _dp,
+                   _dp, _dp, _dp, ctypes.POINTER(ctypes.c_double),
+                   ctypes.POINTER(ctypes.c_int32), _dp, ctypes.c_int]
+    rc = fn(ne, _p(A), _p(I), Z.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _p(w), float(mass),
+            _p(K), n, float(cutoff), int(min_points), ctypes.cast(dcs, vp), ctypes.cast(integral, vp),
+            _p(out["elem"]), _p(out["cs"]), _p(out["cel"]), _p(out["straggling"]), _p(out["csf"]),
+            _p(out["cs_total"]), ctypes.byref(kt), ctypes.byref(it), _p(out["xt"]), int(threads))
+    out["kt"], out["it"], out["rc"] = kt.value, it.value, rc
+    return out
+
+
+def integral_scalar(checker, process, mode, K, xlow, xhigh, element, mass, min_points):
+    """The generalised recoil integral (modes 0 / 1 / 2, upper bound x_high) for every energy."""
+    pre = "oracle_" if checker.kind == "port" else "noa_ref_"
+    fn = getattr(checker._lib, pre + "integral_scalar")
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                   ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_double,
+                   ctypes.c_int32]
+    return np.array([fn(int(process), int(mode), float(k), float(xlow), float(xhigh),
+                        float(element[0]), float(element[1]), int(element[2]), float(mass),
+                        int(min_points)) for k in _f64(K)])
+
+
 def _make(target):
     subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
 

@@ -403,6 +403,47 @@ double oracle_recoil_integral(int process, int integrand, double K, double xlow,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Scalar entry points for material_oracle.c (per-material table assembly).
+ * oracle_integral_scalar generalises the recoil integral the way PUMAS's compute_dcs_integral is
+ * shaped (src/noa/3rdparty/_pumas/pumas.c:10901-10955): an upper bound x_high and a third
+ * integrand, mode 2 = dcs*q*q*q (the straggling integrand, pumas.c:10945-10949), evaluated with
+ * NOA's own composite 6-point rule and Jacobian (src/noa/pms/dcs.hh:89-105).  Modes 0 / 1 with
+ * x_high = 1 are exactly dcs::recoil_integral(f, del|cel_integrand), closed forms included.
+ * ------------------------------------------------------------------------------------------ */
+double oracle_dcs_scalar(int process, double K, double q, double A, double I, int32_t Z,
+                         double mass) {
+    const oracle_element el = {A, I, Z};
+    return pick(process)(K, q, &el, mass);
+}
+
+typedef struct {
+    dcs_fn f;
+    double K, mass;
+    const oracle_element *el;
+    int mode;
+} recoil_mode_ctx;
+
+static double recoil_mode_node(double t, const void *vctx) {
+    const recoil_mode_ctx *c = (const recoil_mode_ctx *) vctx;
+    const double q = exp(t);
+    double y = c->f(c->K, q, c->el, c->mass) * q;
+    if (c->mode > 0) y *= q;
+    if (c->mode > 1) y *= q;
+    return y;
+}
+
+double oracle_integral_scalar(int process, int mode, double K, double xlow, double xhigh, double A,
+                              double I, int32_t Z, double mass, int32_t min_points) {
+    const oracle_element el = {A, I, Z};
+    if (mode <= 1 && xhigh == 1.)
+        return oracle_recoil_integral(process, mode, K, xlow, &el, mass, min_points);
+    recoil_mode_ctx c = {pick(process), K, mass, &el, mode};
+    return composite_gl(log(K * xlow), log(K * xhigh), recoil_mode_node, &c, (uint32_t) min_points,
+                        6, GL6_X, GL6_W) /
+           (K + mass);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Array drivers: dcs::vmap / pvmap (src/noa/pms/dcs.hh:35-75, src/noa/utils/common.hh:146-183)
  * and dcs::vmap_integral (src/noa/pms/dcs.hh:115-130).  `threads` <= 1 is the reference's serial
  * loop; > 1 is its `omp parallel for` (pvmap) or, for integrals, a harness-side loop over energies.

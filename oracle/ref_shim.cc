@@ -93,6 +93,57 @@ int noa_ref_vmap_integral(int process, int integrand, int parallel, const double
     return 1;
 }
 
+// ---- scalar entry points for oracle/material_oracle.c ---------------------
+// The reference's own scalar DCS lambdas and its own quadrature; the mode-2 (straggling) integrand
+// and the upper bound x_high follow PUMAS's compute_dcs_integral (pumas.c:10901-10955) in the shape
+// of dcs::recoil_integral (dcs.hh:89-105).  Modes 0 / 1 with x_high = 1 ARE dcs::recoil_integral.
+double noa_ref_dcs_scalar(int process, double K, double q, double A, double I, int32_t Z,
+                          double mass) {
+    const AtomicElement el{A, I, Z};
+    switch (process) {
+        case 0: return dcs::bremsstrahlung(K, q, el, mass);
+        case 1: return dcs::pair_production(K, q, el, mass);
+        case 2: return dcs::photonuclear(K, q, el, mass);
+        default: return dcs::ionisation(K, q, el, mass);
+    }
+}
+
+}  // extern "C"
+
+namespace {
+    template<typename F>
+    double integral_mode(const F &f, int mode, double K, double xlow, double xhigh,
+                         const AtomicElement &el, double mass, int32_t min_points) {
+        if (mode <= 1 && xhigh == 1.)
+            return (mode == 0)
+                   ? dcs::recoil_integral(f, dcs::del_integrand)(K, xlow, el, mass, min_points)
+                   : dcs::recoil_integral(f, dcs::cel_integrand)(K, xlow, el, mass, min_points);
+        return noa::utils::numerics::quadrature6<Scalar>(
+                log(K * xlow), log(K * xhigh),
+                [&](const Scalar &t) {
+                    const Scalar q = exp(t);
+                    Scalar y = f(K, q, el, mass) * q;
+                    if (mode > 0) y *= q;
+                    if (mode > 1) y *= q;
+                    return y;
+                },
+                min_points) / (K + mass);
+    }
+}
+
+extern "C" {
+
+double noa_ref_integral_scalar(int process, int mode, double K, double xlow, double xhigh,
+                               double A, double I, int32_t Z, double mass, int32_t min_points) {
+    const AtomicElement el{A, I, Z};
+    switch (process) {
+        case 0: return integral_mode(dcs::bremsstrahlung, mode, K, xlow, xhigh, el, mass, min_points);
+        case 1: return integral_mode(dcs::pair_production, mode, K, xlow, xhigh, el, mass, min_points);
+        case 2: return integral_mode(dcs::photonuclear, mode, K, xlow, xhigh, el, mass, min_points);
+        default: return integral_mode(dcs::ionisation, mode, K, xlow, xhigh, el, mass, min_points);
+    }
+}
+
 // ---- Coulomb and soft scattering ------------------------------------
 int noa_ref_coulomb_data(double *fcm, double *screening, double *fspin, double *invlambda,
                          const double *K, int64_t n, double A, double I, int32_t Z, double mass) {
