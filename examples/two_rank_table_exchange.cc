@@ -66,8 +66,13 @@ static int run_rank(int rank, int sock) {
     CHECK(cudaMalloc(&d_K_local, K_local.size() * sizeof(double)));
     CHECK(cudaMalloc(&d_K, n * sizeof(double)));
     CHECK(cudaMalloc(&d_ref, table_doubles * sizeof(double)));
-    CHECK(cudaMalloc(&d_sync, 8 * sizeof(uint32_t)));
-    CHECK(cudaMemset(d_sync, 0, 8 * sizeof(uint32_t)));
+    const size_t sync_words = 8 + 4 * K_local.size();     // see noa_dcs_table_exchange_f64
+    CHECK(cudaMalloc(&d_sync, sync_words * sizeof(uint32_t)));
+    CHECK(cudaMemset(d_sync, 0, sync_words * sizeof(uint32_t)));
+    // optional: lets the build cut rows into pieces when a rank has few waves of heavy rows
+    const int64_t scratch_doubles = 4 * (int64_t) K_local.size() * 6 * ((min_points + 5) / 6);
+    double *d_scratch = nullptr;
+    CHECK(cudaMalloc(&d_scratch, scratch_doubles * sizeof(double)));
     CHECK(cudaMemcpy(d_K_local, K_local.data(), K_local.size() * sizeof(double),
                      cudaMemcpyHostToDevice));
     CHECK(cudaMemcpy(d_K, K.data(), n * sizeof(double), cudaMemcpyHostToDevice));
@@ -90,7 +95,8 @@ static int run_rank(int rank, int sock) {
         }
         CHECK(noa_dcs_table_exchange_f64(0xF, d_K_local, (int64_t) K_local.size(), xlow,
                                          min_points, A, I, Z, mass, world, rank, del, cel, flags,
-                                         d_sync, epoch, n, /*first_row=*/rank,
+                                         d_sync, d_scratch, scratch_doubles, epoch, n,
+                                         /*first_row=*/rank,
                                          /*row_stride=*/world, /*timeout_seconds=*/20., stream));
         CHECK(cudaStreamSynchronize(stream));
         CHECK(cudaMemcpy(got.data(), mine + off, table_doubles * sizeof(double),

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define NOA_DCS_ABI_VERSION 2
+#define NOA_DCS_ABI_VERSION 3
 
 /* process ids: PUMAS / NOA order (NPR = 4, src/noa/pms/physics.hh:86) */
 #define NOA_DCS_BREMSSTRAHLUNG 0
@@ -110,6 +110,23 @@ int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double
                       double *cel, void *stream);
 
 /*
+ * noa_dcs_table_f64 with a caller-provided workspace for the node terms ("flat" form): every
+ * (row, node) of a process is evaluated as one flat index space by a persistent grid (no barrier,
+ * no per-row summation phase, balanced to 256 nodes whatever the number of rows), the two terms of
+ * a node make one round trip through `workspace`, and one summation kernel adds each row's terms
+ * up in node order (numerics.hh:84-87) -- the same additions in the same order, so the same bits
+ * as noa_dcs_table_f64.  `workspace` = device array of at least
+ * noa_dcs_table_workspace_doubles(nK, min_points) doubles (2 nK + 8 nK * 6 ceil(min_points / 6):
+ * 16 B per node and process), contents irrelevant, free again when the launches have run on
+ * `stream`.  A NULL or too small workspace falls back to noa_dcs_table_f64's launches.
+ */
+int64_t noa_dcs_table_workspace_doubles(int64_t nK, int32_t min_points);
+int noa_dcs_table_ws_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                         int32_t min_points, double A, double I, int32_t Z, double mass,
+                         double *del, double *cel, double *workspace, int64_t workspace_doubles,
+                         void *stream);
+
+/*
  * Tables of a material (mass-fraction mix of elements): table[c][p][i] = sum_e t_e[c][p][i] * w[e]
  * with t_e the element tables of noa_dcs_table_f64 (c = 0 DEL, 1 CEL), accumulated in composition
  * order from 0 -- the per-element mixing PUMAS applies to its cross-section and energy-loss
@@ -148,8 +165,13 @@ int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int6
  * enqueued after the call on `stream` sees the complete table.  `epoch` must increase by one per
  * call on all ranks (flags start at 0, first epoch 1); callers alternate between two destination
  * tables so a fast rank never overwrites rows a slow rank is still reading.
- * `sync` = EIGHT zero-initialised 32-bit words on this device {CTA counter, timeout count, 2
- * reserved, 4 row queues}.  A peer that does not arrive within `timeout_seconds` of wall-clock time
+ * `sync` = 8 + 4 * n_local zero-initialised 32-bit words on this device {CTA counter, timeout
+ * count, 2 reserved, 4 row queues, then one arrival word per (process, local row)}.
+ * `scratch` (optional, may be NULL) = workspace of noa_dcs_table_ws_f64 for the LOCAL rows
+ * (scratch_doubles >= noa_dcs_table_workspace_doubles(n_local, min_points)): the build then runs
+ * in the flat form, whose summation kernel stores the finished rows to every peer and whose last
+ * CTA runs the flag exchange -- one rank of eight holds 1 250 rows per process on config 4, too few
+ * waves for the row-per-CTA forms.  Without it: persistent CTAs pulling rows from the queues.  A peer that does not arrive within `timeout_seconds` of wall-clock time
  * (<= 0: NOA_DCS_DEFAULT_EXCHANGE_TIMEOUT_S) is FATAL: the timeout count is bumped and the kernel
  * traps, so the stream reports a launch failure instead of handing back a partial table.
  */
@@ -157,9 +179,10 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
                                double xlow, int32_t min_points, double A, double I, int32_t Z,
                                double mass, int32_t n_peers, int32_t my_peer,
                                double *const *peer_del, double *const *peer_cel,
-                               uint32_t *const *peer_flags, uint32_t *sync, uint32_t epoch,
-                               int64_t n_total, int64_t first_row, int64_t row_stride,
-                               double timeout_seconds, void *stream);
+                               uint32_t *const *peer_flags, uint32_t *sync, double *scratch,
+                               int64_t scratch_doubles, uint32_t epoch, int64_t n_total,
+                               int64_t first_row, int64_t row_stride, double timeout_seconds,
+                               void *stream);
 
 /*
  * The exchange SURVEY.md 8(b) sketches for hosts that hold an NCCL communicator instead of

@@ -45,7 +45,11 @@ SIGNATURES = {
     "noa_dcs_table_exchange_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
                                                   _i32, _f64, _i32, _i32, ctypes.POINTER(_vp),
                                                   ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp,
-                                                  ctypes.c_uint32, _i64, _i64, _i64, _f64, _vp]),
+                                                  _vp, _i64, ctypes.c_uint32, _i64, _i64, _i64,
+                                                  _f64, _vp]),
+    "noa_dcs_table_workspace_doubles": (_i64, [_i64, _i32]),
+    "noa_dcs_table_ws_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64, _i32,
+                                            _f64, _vp, _vp, _vp, _i64, _vp]),
     "noa_dcs_allgather_f64": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "noa_dcs_vmap_integral_f64": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64, _f64,
                                                  _i32, _f64, _f64, _i32, _f64, _vp]),
@@ -111,7 +115,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.noa_dcs_abi_version() != 2:
+    if lib.noa_dcs_abi_version() != 3:
         raise NoaDcsError("libnoa_dcs_b200.so ABI version mismatch")
     bad = _i64(0)
     if lib.noa_dcs_selfcheck(ctypes.byref(bad)) != 0:

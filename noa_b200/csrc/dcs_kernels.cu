@@ -29,6 +29,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <utility>
 
 #include "../../include/noa_dcs_b200.h"
 #include "dcs_device.cuh"
@@ -349,7 +350,104 @@ struct TableOptions {
     double xhigh = 1.;
     int32_t second_power = 2;
     bool quadrature_only = false;
+    double *workspace = nullptr;        // node terms of the flat form (table_kernels.cuh)
+    int64_t workspace_doubles = 0;
 };
+
+static int64_t table_nodes(int32_t min_points) { return ((int64_t) min_points + 5) / 6 * 6; }
+
+// {ln(K xlow), h} per row + 4 queue words + 4 processes x nK rows x nodes x {DEL term, CEL term}
+static int64_t table_workspace_doubles(int64_t nK, int32_t min_points) {
+    if (nK <= 0 || min_points < 1) return 0;
+    return 2 * nK + 2 + 8 * nK * table_nodes(min_points);
+}
+
+template <typename... KArgs, typename... Args>
+static int launch_chained(void (*kernel)(KArgs...), unsigned grid, unsigned block, bool dependent,
+                          cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (dependent) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) return (int) e;
+    return after_launch();
+}
+
+template <int PROCESS>
+static int launch_terms(const double *K, int64_t nK, const double2 *rowpar, double2 *terms,
+                        double2 *terms_b, uint32_t *queue, const FlatPlan &fp, const Params &p,
+                        bool dependent, cudaStream_t s) {
+    int blocks = 0;
+    int rc = persistent_grid(table_terms_kernel<PROCESS>, nK * (int64_t) fp.cells * 6, blocks);
+    if (rc) return rc;
+    return launch_chained(table_terms_kernel<PROCESS>, (unsigned) blocks, kThreads, dependent, s, K,
+                          nK, rowpar, terms, terms_b, queue, fp, p);
+}
+
+// The flat form of a table build (table_kernels.cuh): row parameters, one terms kernel per
+// process (heaviest first), one summation kernel that also delivers the rows -- to the peers too,
+// rank barrier included, in the exchange form.
+static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                           int32_t min_points, const Params &p, TableOut out, cudaStream_t s,
+                           const TableOptions &opt) {
+    FlatPlan fp{};
+    fp.cells = ((uint32_t) min_points + 5u) / 6u;
+    fp.second_power = opt.second_power;
+    fp.quadrature_only = opt.quadrature_only ? 1 : 0;
+    fp.xlow = xlow;
+    fp.xhigh = opt.xhigh;
+    const int64_t nodes = table_nodes(min_points);
+    double2 *rowpar = reinterpret_cast<double2 *>(opt.workspace);
+    uint32_t *queues = reinterpret_cast<uint32_t *>(rowpar + nK);
+    double2 *terms = rowpar + nK + 1;
+    table_rowpar_kernel<<<(unsigned) ((nK + 255) / 256), 256, 0, s>>>(K, nK, fp, rowpar, queues);
+    int rc = after_launch();
+    if (rc) return rc;
+    static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
+                                       NOA_DCS_BREMSSTRAHLUNG, NOA_DCS_IONISATION};
+    FlatSum fs{};
+    fs.quadrature_only = fp.quadrature_only;
+    fs.xlow = xlow;
+    bool launched = false;
+    for (int i = 0; i < 4; i++) {
+        const int pr = heavy_first[i];
+        if (!((process_mask >> pr) & 1u)) continue;
+        const int slot = fs.n_slots++;
+        double2 *t = terms + (int64_t) slot * nK * nodes;
+        fs.process[slot] = pr;
+        fs.out_row[slot] = pr;
+        fs.terms[slot] = t;
+        // bremsstrahlung and ionisation together go through one fused launch (heavy_first ends
+        // with bremsstrahlung, ionisation: their slots are adjacent)
+        const bool both_light = (process_mask & 9u) == 9u;
+        if (pr == NOA_DCS_IONISATION && both_light) continue;      // done with bremsstrahlung
+        const bool dep = launched;
+        if (pr == NOA_DCS_BREMSSTRAHLUNG && both_light)
+            rc = launch_terms<4>(K, nK, rowpar, t, t + nK * nodes, queues + slot, fp, p, dep, s);
+        else
+            switch (pr) {
+                case 0: rc = launch_terms<0>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
+                case 1: rc = launch_terms<1>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
+                case 2: rc = launch_terms<2>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
+                default: rc = launch_terms<3>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
+            }
+        if (rc) return rc;
+        launched = true;
+    }
+    const int64_t chains = nK * fs.n_slots;
+    const unsigned grid = (unsigned) ((chains + kSumWarps - 1) / kSumWarps);
+    out.total_ctas = grid;
+    return launch_chained(table_sum_kernel, grid, 32u * kSumWarps, true, s, K, nK,
+                          (uint32_t) nodes, fs, p, out);
+}
 
 static int table_impl(unsigned process_mask, bool single_row, const double *K, int64_t nK,
                       double xlow, int32_t min_points, double A, double I, int32_t Z, double mass,
@@ -378,6 +476,10 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
         rc = after_launch();
         if (rc) return rc;
     }
+
+    if (!single_row && opt.workspace &&
+        opt.workspace_doubles >= table_workspace_doubles(nK, min_points))
+        return table_flat_impl(process_mask, K, nK, xlow, min_points, p, out, s, opt);
 
     static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
                                        NOA_DCS_BREMSSTRAHLUNG, NOA_DCS_IONISATION};
@@ -562,6 +664,21 @@ int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double
                       local_out(del, cel, nK), stream);
 }
 
+int64_t noa_dcs_table_workspace_doubles(int64_t nK, int32_t min_points) {
+    return table_workspace_doubles(nK, min_points);
+}
+
+int noa_dcs_table_ws_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
+                         int32_t min_points, double A, double I, int32_t Z, double mass,
+                         double *del, double *cel, double *workspace, int64_t workspace_doubles,
+                         void *stream) {
+    TableOptions opt;
+    opt.workspace = workspace;
+    opt.workspace_doubles = workspace_doubles;
+    return table_impl(process_mask, false, K, nK, xlow, min_points, A, I, Z, mass,
+                      local_out(del, cel, nK), stream, opt);
+}
+
 int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
                                int32_t min_points, int32_t n_elements, const double *A,
                                const double *I, const int32_t *Z, const double *w, double mass,
@@ -615,9 +732,10 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
                                double xlow, int32_t min_points, double A, double I, int32_t Z,
                                double mass, int32_t n_peers, int32_t my_peer,
                                double *const *peer_del, double *const *peer_cel,
-                               uint32_t *const *peer_flags, uint32_t *sync, uint32_t epoch,
-                               int64_t n_total, int64_t first_row, int64_t row_stride,
-                               double timeout_seconds, void *stream) {
+                               uint32_t *const *peer_flags, uint32_t *sync, double *scratch,
+                               int64_t scratch_doubles, uint32_t epoch, int64_t n_total,
+                               int64_t first_row, int64_t row_stride, double timeout_seconds,
+                               void *stream) {
     if (n_peers < 1 || n_peers > NOA_DCS_MAX_PEERS || my_peer < 0 || my_peer >= n_peers)
         return NOA_DCS_EINVAL;
     if (!peer_del || !peer_cel || !peer_flags || !sync) return NOA_DCS_EINVAL;
@@ -639,8 +757,11 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
         out.cel[j] = peer_cel[j];
         out.flags[j] = peer_flags[j];
     }
+    TableOptions opt;
+    opt.workspace = scratch;
+    opt.workspace_doubles = scratch_doubles;
     return table_impl(process_mask, false, K_local, n_local, xlow, min_points, A, I, Z, mass, out,
-                      stream);
+                      stream, opt);
 }
 
 int noa_dcs_vmap_integral_f64(int process, int integrand, const double *K, double *result,

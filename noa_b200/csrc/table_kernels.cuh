@@ -162,6 +162,28 @@ __device__ __noinline__ double dcs_value_call(double K, double q, const Params &
     return dcs_value<PROCESS, true>(K, q, p, T);
 }
 
+// The two terms of node i of a row (dcs.hh:107-113; numerics.hh:84-87): f q h w and f q q h w.
+template <int PROCESS>
+__device__ __forceinline__ void table_node_terms(uint32_t i, double k, double lb, double h,
+                                                 const TablePlan &plan, const Params &p,
+                                                 const glibm::Tab &T, const double2 *gl6,
+                                                 double &td, double &tc) {
+    const uint32_t cell = i / 6u;
+    const uint32_t j = i - cell * 6u;
+    const double2 xw = gl6[j];
+    const double x = lb + h * (cell + xw.x);
+    const double q = glibm::exp(x, T);
+    const double f = (NOA_TABLE_EVAL_CALL && (PROCESS == 1 || PROCESS == 2))
+                             ? dcs_value_call<PROCESS>(k, q, p, T)
+                             : dcs_value<PROCESS, true>(k, q, p, T);
+    const double w = xw.y;
+    const double fq = f * q;
+    td = fq * h * w;                        // del_integrand, dcs.hh:107-109
+    double y = fq * q;                      // cel_integrand, dcs.hh:111-113
+    if (plan.second_power == 3) y *= q;     // straggling, pumas.c:10945-10949
+    tc = y * h * w;
+}
+
 // One item: rows nK-1 - (item R + r), r = 0 .. R-1, of `PROCESS` (descending energy).  Called by
 // every thread of the CTA with the shared buffers free to overwrite.
 template <int PROCESS>
@@ -227,23 +249,9 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
                         }
                 }
                 if (!s.row_quad[r]) continue;
-                const uint32_t i = base + il;
-                const uint32_t cell = i / 6u;
-                const uint32_t j = i - cell * 6u;
-                const double h = s.row_h[r];
-                const double k = s.row_k[r];
-                const double2 xw = s.gl6[j];
-                const double x = s.row_lb[r] + h * (cell + xw.x);
-                const double q = glibm::exp(x, T);
-                const double f = (NOA_TABLE_EVAL_CALL && (PROCESS == 1 || PROCESS == 2))
-                                         ? dcs_value_call<PROCESS>(k, q, p, T)
-                                         : dcs_value<PROCESS, true>(k, q, p, T);
-                const double w = xw.y;
-                const double fq = f * q;
-                const double td = fq * h * w;           // del_integrand, dcs.hh:107-109
-                double y = fq * q;                      // cel_integrand, dcs.hh:111-113
-                if (plan.second_power == 3) y *= q;     // straggling, pumas.c:10945-10949
-                const double tc = y * h * w;
+                double td, tc;
+                table_node_terms<PROCESS>(base + il, s.row_k[r], s.row_lb[r], s.row_h[r], plan, p,
+                                          T, s.gl6, td, tc);
                 s.terms[il * CH + 2 * r] = td;
                 s.terms[il * CH + 2 * r + 1] = tc;
                 if (td != 0. || tc != 0.) {             // NaN counts as non-zero
@@ -296,13 +304,14 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
 
 template <unsigned MASK>
 struct TableMinBlocks {
-    static constexpr int value = (MASK == 2u)   ? NOA_MINB_TABLE_PAIR
+    static constexpr int value = (MASK == 9u)   ? NOA_MINB_TABLE_LIGHT
+                                 : (MASK == 2u) ? NOA_MINB_TABLE_PAIR
                                  : (MASK == 4u) ? NOA_MINB_TABLE_PHOTO
                                  : (MASK == 15u) ? NOA_MINB_TABLE_ALL
                                                  : NOA_MINB_TABLE_LIGHT;
 };
 
-template <unsigned MASK>
+template <unsigned MASK, bool PERSISTENT>
 __device__ __forceinline__ void table_dispatch(uint32_t b, const double *__restrict__ K, int64_t nK,
                                                const TableOut &out, const TablePlan &plan,
                                                const Params &p, const glibm::Tab &T, TableShared &s,
@@ -314,10 +323,14 @@ __device__ __forceinline__ void table_dispatch(uint32_t b, const double *__restr
             if (MASK & 1u) table_item<0>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
             break;
         case 1:
-            if (MASK & 2u) table_item<1>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            if (MASK & 2u) {
+                table_item<1>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            }
             break;
         case 2:
-            if (MASK & 4u) table_item<2>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            if (MASK & 4u) {
+                table_item<2>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            }
             break;
         default:
             if (MASK & 8u) table_item<3>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
@@ -346,15 +359,246 @@ table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ T
             __syncthreads();                   // s.next[cur] written; shared buffers free again
             const uint32_t b = s.next[cur];
             if (b >= total) break;
-            table_dispatch<MASK>(b, K, nK, out, plan, p, T, s, queue, &s.next[cur ^ 1]);
+            table_dispatch<MASK, true>(b, K, nK, out, plan, p, T, s, queue, &s.next[cur ^ 1]);
         }
     } else {
-        table_dispatch<MASK>(blockIdx.x, K, nK, out, plan, p, T, s, nullptr, nullptr);
+        table_dispatch<MASK, false>(blockIdx.x, K, nK, out, plan, p, T, s, nullptr, nullptr);
         // scatter form without flags: the writer lanes fence their own remote stores
         if (out.n_peers > 1 && out.flags[0] == nullptr && threadIdx.x < 32) __threadfence_system();
     }
     // completion order along the chain: this kernel does not retire before its predecessor has
     if (threadIdx.x == 0) pdl_wait_prerequisites();
+    if (out.flags[0] != nullptr) table_exchange_tail(out);
+}
+
+// bremsstrahlung (td, tc) and, if `ion`, ionisation (ud, uc) terms of one node
+__device__ __forceinline__ void table_node_terms_light(uint32_t i, double k, double lb, double h,
+                                                       bool ion, const TablePlan &plan,
+                                                       const Params &p, const glibm::Tab &T,
+                                                       const double2 *gl6, double &td, double &tc,
+                                                       double &ud, double &uc) {
+    const uint32_t cell = i / 6u;
+    const uint32_t j = i - cell * 6u;
+    const double2 xw = gl6[j];
+    const double x = lb + h * (cell + xw.x);
+    const double q = glibm::exp(x, T);
+    const double w = xw.y;
+    {
+        const double fq = dcs_value<0, true>(k, q, p, T) * q;
+        td = fq * h * w;
+        double y = fq * q;
+        if (plan.second_power == 3) y *= q;
+        tc = y * h * w;
+    }
+    if (ion) {
+        const double fq = dcs_value<3, true>(k, q, p, T) * q;
+        ud = fq * h * w;
+        double y = fq * q;
+        if (plan.second_power == 3) y *= q;
+        uc = y * h * w;
+    }
+}
+
+// ---- flat form (builds that come with a workspace for the node terms) ----------------------------
+// With 16 B of workspace per node the rows need no CTA-per-row structure at all:
+//   table_rowpar_kernel      {ln(K xlow), h} of every row
+//   table_terms_kernel<P>    every (row, node) of process P as one flat index space, 256
+//                            consecutive nodes per CTA iteration, chunks dealt round-robin to a
+//                            persistent grid: no barrier, no summation phase, warps never wait for
+//                            each other, and the schedule is balanced to a 256-node chunk whatever
+//                            the number of rows -- one rank of eight has 1 250 rows per process,
+//                            where the row-per-CTA forms leave the two cheap processes
+//                            latency-bound on a partial wave and the heavy ones ragged;
+//   table_sum_kernel         one warp per (process, row): coalesced 512-byte reads of the terms,
+//                            res += term in node order by shuffle broadcast (every lane carries
+//                            both running sums), / (K + mass) -- or the closed form of an
+//                            ionisation row -- stored to the local table and every peer's; in the
+//                            exchange form its last CTA runs the rank barrier.
+// The launches of a build are chained with programmatic dependent launch.  The terms make one
+// round trip through L2 / HBM (160 MB each way per process on config 4, hidden under the
+// FP64-bound evaluation); what is bought is the 4.4 us of two-lane summation per row during which
+// the other 254 threads of the row's CTA idled (barrier stalls: 14 % of the pair kernel's warp
+// cycles, 8 % of photonuclear's, profiles/r02_ncu_full_s3.md).
+struct FlatPlan {
+    uint32_t cells;
+    int32_t second_power;
+    int32_t quadrature_only;
+    double xlow, xhigh;
+};
+
+// queue words of the flat form live in the workspace right behind rowpar; table_rowpar_kernel
+// zeroes them
+__global__ void table_rowpar_kernel(const double *__restrict__ K, int64_t nK,
+                                    const __grid_constant__ FlatPlan plan,
+                                    double2 *__restrict__ rowpar, uint32_t *__restrict__ queues) {
+    __shared__ glibm::Tables s_tables;
+    const glibm::Tab T = stage_tables(s_tables);
+    const int64_t row = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < 4) queues[row] = 0;
+    if (row >= nK) return;
+    const double k = K[row];
+    const double lb = glibm::log(k * plan.xlow, T);
+    const double ub = (plan.xhigh == 1.) ? glibm::log(k, T) : glibm::log(k * plan.xhigh, T);
+    rowpar[row] = make_double2(lb, (ub - lb) / plan.cells);
+}
+
+// Work unit = kFlatUnit x 32 consecutive nodes of one row, popped by a WARP from a device-side
+// queue (lane 0's atomic, one unit ahead so its latency is hidden): heaviest rows first, no
+// barrier anywhere, no static assignment whose period could lock onto the rows'.
+// PROCESS = 4: bremsstrahlung and ionisation of a node in one pass (one exp, two independent
+// integrands to interleave, one launch less -- a rank with few rows pays a wave of latency per
+// launch); `terms` then holds the bremsstrahlung terms and `terms_b` the ionisation ones.
+template <int PROCESS>
+struct FlatCfg {
+    static constexpr uint32_t unit = (PROCESS == 1 || PROCESS == 2) ? 1u : 8u;
+    static constexpr unsigned mask = (PROCESS == 4) ? 9u : (1u << PROCESS);
+};
+
+template <int PROCESS>
+__global__ void __launch_bounds__(kThreads, TableMinBlocks<FlatCfg<PROCESS>::mask>::value)
+table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__restrict__ rowpar,
+                   double2 *__restrict__ terms, double2 *__restrict__ terms_b,
+                   uint32_t *__restrict__ queue, const __grid_constant__ FlatPlan fp,
+                   const __grid_constant__ Params p) {
+    __shared__ StagedShared s_staged;
+    __shared__ double2 s_gl6[6];
+    if (threadIdx.x < 6)
+        s_gl6[threadIdx.x] = make_double2(c_gl6_x[threadIdx.x], c_gl6_w[threadIdx.x]);
+    const glibm::Tab T = stage_all(s_staged, p);
+    // the next launch of the build (another process: other terms) may fill SMs as they free up;
+    // rowpar was complete before the first terms kernel of the build started (stream order)
+    pdl_release_dependents();
+    TablePlan plan{};
+    plan.second_power = fp.second_power;
+    const uint32_t nodes = fp.cells * 6u;
+    constexpr uint32_t span = 32u * FlatCfg<PROCESS>::unit;
+    const uint32_t per_row = (nodes + span - 1) / span;
+    const uint64_t units = (uint64_t) nK * per_row;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(queue, 1u);
+    for (;;) {
+        const uint32_t u = __shfl_sync(0xffffffffu, next, 0);
+        if (u >= units) break;
+        if (lane == 0) next = atomicAdd(queue, 1u);
+        const uint32_t rr = u / per_row;
+        const int64_t row = nK - 1 - (int64_t) rr;      // descending energy: the schedule ends cheap
+        const double k = K[row];
+        // dcs.hh:963-966, 987-990: closed form, nothing to integrate
+        const bool ion_closed = k <= p.i_kthr && !fp.quadrature_only;
+        if (PROCESS == 3 && ion_closed) continue;
+        const double2 lbh = __ldcg(rowpar + row);
+        double2 *row_terms = terms + row * nodes;
+        const uint32_t first = (u - rr * per_row) * span + lane;
+#pragma unroll 1
+        for (uint32_t i = first; i < min(nodes, first + span); i += 32u) {
+            double td, tc;
+            if (PROCESS == 4) {
+                double ud = 0., uc = 0.;
+                table_node_terms_light(i, k, lbh.x, lbh.y, !ion_closed, plan, p, T, s_gl6, td, tc,
+                                       ud, uc);
+                if (!ion_closed) terms_b[row * nodes + i] = make_double2(ud, uc);
+            } else {
+                table_node_terms<(PROCESS == 4 ? 0 : PROCESS)>(i, k, lbh.x, lbh.y, plan, p, T,
+                                                                s_gl6, td, tc);
+            }
+            row_terms[i] = make_double2(td, tc);
+        }
+    }
+    // completion order along the chain: this kernel does not retire before its predecessor has,
+    // so the summation kernel only has to wait for the last one
+    __syncthreads();
+    if (threadIdx.x == 0) pdl_wait_prerequisites();
+}
+
+struct FlatSum {
+    int32_t n_slots;
+    int32_t process[4];
+    int32_t out_row[4];             // output row of slot s
+    const double2 *terms[4];        // [nK][nodes]
+    int32_t quadrature_only;
+    double xlow;
+};
+
+// One WARP per (process, row).  The row's terms stream through a private shared-memory ring
+// (cp.async, kSumStage nodes = 4 KB per stage, the next stage in flight while this one is added
+// up: enough bytes in flight per SM to keep HBM busy with a few thousand rows, and a row costs
+// its chain of additions -- 4.4 us at 1002 nodes -- plus one stage of latency however few rows
+// there are).  Lanes 0 and 1 own the two chains: res += f(x) h w[j] in node order
+// (numerics.hh:84-87).
+constexpr int kSumWarps = 4;
+constexpr uint32_t kSumStage = 256;
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kSumWarps)
+table_sum_kernel(const double *__restrict__ K, int64_t nK, uint32_t nodes,
+                 const __grid_constant__ FlatSum fs, const __grid_constant__ Params p,
+                 const __grid_constant__ TableOut out) {
+    __shared__ glibm::Tables s_tables;
+    __shared__ double2 s_ring[kSumWarps][2][kSumStage];
+    const glibm::Tab T = stage_tables(s_tables);     // for the closed-form rows
+    pdl_wait_prerequisites();       // every terms kernel of the build has completed
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t w = threadIdx.x >> 5;
+    const int64_t chain = (int64_t) blockIdx.x * kSumWarps + w;
+    if (chain < nK * fs.n_slots) {
+        const int slot = (int) (chain / nK);
+        const int64_t row = nK - 1 - (chain - (int64_t) slot * nK);
+        const double k = K[row];
+        const bool closed = fs.process[slot] == 3 && k <= p.i_kthr && !fs.quadrature_only;
+        double acc = 0.;
+        if (!closed) {
+            const double2 *t = fs.terms[slot] + row * nodes;
+            const uint32_t ring = (uint32_t) __cvta_generic_to_shared(&s_ring[w][0][0]);
+            const uint32_t n_stages = (nodes + kSumStage - 1) / kSumStage;
+            auto fetch = [&](uint32_t st) {
+                const uint32_t base = st * kSumStage;
+                const uint32_t dst = ring + (st & 1u) * kSumStage * 16u;
+#pragma unroll
+                for (uint32_t e = 0; e < kSumStage; e += 32u)
+                    if (base + e + lane < nodes) cp_async_16(dst + (e + lane) * 16u, t + base + e + lane);
+                cp_async_commit();
+            };
+            fetch(0);
+            for (uint32_t st = 0; st < n_stages; st++) {
+                if (st + 1 < n_stages) {
+                    fetch(st + 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+                if (lane < 2) {
+                    const double *src = reinterpret_cast<const double *>(&s_ring[w][st & 1u][0]) + lane;
+                    const uint32_t count = min(kSumStage, nodes - st * kSumStage);
+#pragma unroll 8
+                    for (uint32_t il = 0; il < count; il++) acc += src[2 * il];
+                }
+                __syncwarp();       // the stage may be overwritten by the fetch after next
+            }
+        }
+        if (lane < 2) {
+            double *const *dst = lane ? out.cel : out.del;
+            if (dst[0] != nullptr) {
+                const double v = closed ? ionisation_closed_form(k, fs.xlow, (int) lane, p, T)
+                                        : acc / (k + p.mass);
+                const int64_t at = (int64_t) fs.out_row[slot] * out.n_total + out.first_row +
+                                   row * out.row_stride;
+                for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
+                // scatter form without flags: the writer lanes fence their own remote stores
+                if (out.n_peers > 1 && out.flags[0] == nullptr) __threadfence_system();
+            }
+        }
+    }
     if (out.flags[0] != nullptr) table_exchange_tail(out);
 }
 

@@ -210,8 +210,11 @@ class PeerTableBuilder(_HostTables):
         self._del = [(vp * world)(*[p + b * per_table * 8 for p in ptrs]) for b in range(2)]
         self._cel = [(vp * world)(*[p + b * per_table * 8 + half for p in ptrs]) for b in range(2)]
         self._flags = (vp * world)(*[p + 2 * per_table * 8 for p in ptrs])
-        # {CTA counter, timeouts, 2 reserved, 4 row queues} (noa_dcs_table_exchange_f64: `sync`)
-        self.done = torch.zeros(8, dtype=torch.int32, device=K.device)
+        # {CTA counter, timeouts, 2 reserved, 4 row queues, a hand-over word per (process, local row)}
+        # (noa_dcs_table_exchange_f64: `sync`)
+        self.done = torch.zeros(8 + 4 * self.n_local, dtype=torch.int32, device=K.device)
+        # workspace of the flat form (node terms), sized at the first build
+        self.scratch = None
         self.epoch = 0
         torch.cuda.synchronize(K.device)
         if arm:
@@ -238,10 +241,14 @@ class PeerTableBuilder(_HostTables):
         with torch.cuda.device(dev):
             stream = c.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             if self.fused_barrier:
+                need = int(self.lib.noa_dcs_table_workspace_doubles(self.n_local, int(min_points)))
+                if self.scratch is None or self.scratch.numel() < need:
+                    self.scratch = torch.empty(need, dtype=torch.float64, device=dev)
                 self._lib.check(self.lib.noa_dcs_table_exchange_f64(
                     mask, c.c_void_p(self.K_local.data_ptr()), self.n_local, float(xlow),
                     int(min_points), float(A), float(I), int(Z), float(mass), self.world, self.rank,
                     self._del[b], self._cel[b], self._flags, c.c_void_p(self.done.data_ptr()),
+                    c.c_void_p(self.scratch.data_ptr()), self.scratch.numel(),
                     self.epoch, self.n, self.rank, self.world, self.timeout_s, stream))
             else:
                 # peers must be done reading this table before anyone overwrites it

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/noa_dcs_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in noa_b200/_lib.py"
-    assert lib.noa_dcs_abi_version() == 2
+    assert lib.noa_dcs_abi_version() == 3
     assert b"invalid" in lib.noa_dcs_strerror(-1)
     # measurement hooks are not part of the product library any more
     for name in ("noa_dcs_set_pair_mode", "noa_dcs_set_exchange_fence_mode",

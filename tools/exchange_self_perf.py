@@ -19,11 +19,12 @@ for W in (1, 2, 4, 8):
     flags = torch.zeros(16, dtype=torch.int32, device="cuda")
     sync = torch.zeros(8 + 4 * n, dtype=torch.int32, device="cuda")
     dl = (vp * 1)(table.data_ptr()); cl = (vp * 1)(table.data_ptr() + 4 * n * 8); fl = (vp * 1)(flags.data_ptr())
+    scratch = torch.empty(2 * n + 8 * n * 1002, dtype=torch.float64, device="cuda")
     epoch = [0]
     def build():
         epoch[0] += 1
         _lib.check(lib.noa_dcs_table_exchange_f64(15, vp(Kl.data_ptr()), n, 0.05, 1000, 22., 0.1364e-6, 11, MUON_MASS,
-                   1, 0, dl, cl, fl, vp(sync.data_ptr()), epoch[0], n, 0, 1, 10.0,
+                   1, 0, dl, cl, fl, vp(sync.data_ptr()), vp(scratch.data_ptr()), scratch.numel(), epoch[0], n, 0, 1, 10.0,
                    vp(torch.cuda.current_stream().cuda_stream)))
     for _ in range(3): build()
     torch.cuda.synchronize(); ts = []
