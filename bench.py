@@ -25,11 +25,12 @@ barrier + synchronize on both sides, max over ranks).  --workload pair keeps rou
              the table against the compiled reference (oracle/_ref, or the C port where it is
              absent) on rank 0; at N > 1 every rank bit-compares its exchanged table with a local
              single-GPU build.  The extras carry their own parity samples.
-  roofline   the build is FP64-pipe bound.  `frac` = algorithmic FP64-pipe instructions (SURVEY
-             8(d) census per DCS value x the node evaluations INSIDE each process's kinematic
-             range, counted live, + 20 per node) / build time / the DFMA rate measured live by the
-             probe library; `frac_executed` = the FP64 instructions the kernels really execute
-             (ncu counters of this commit, profiles/latest_traffic.json) on the same denominators.
+  roofline   the build is FP64-pipe bound.  `frac` (= `frac_executed`) = the FP64 instructions
+             the kernels of one build really execute (ncu counters of this commit,
+             profiles/latest_traffic.json) / build time / the DFMA rate measured live by the probe
+             library, i.e. the FP64 pipe utilisation over the build; `frac_census` = the same with
+             SURVEY 8(d)'s census (per DCS value x the node evaluations INSIDE each process's
+             kinematic range, counted live, + 20 per node), which over-counts (libdevice prices).
   cpu_baseline  the reference's own table integrals on the host cores (bounded sample).
 --impl reference times only the CPU reference arm on the same config and prints its line.
 """
@@ -577,18 +578,31 @@ def headline_table(c):
         achieved = algo * 2 / per_gpu_s / 1e12
         peak = c.fp64_peak * 2 / 1e12
         executed = c.profile.get("table_build_fp64_instr_executed")
+        frac_executed = (executed / per_gpu_s / c.fp64_peak) if executed else None
+        # `frac` is the executed-instruction fraction (FP64 pipe utilisation over the build):
+        # the census of SURVEY 8(d) prices exp / log / division at libdevice cost and credits the
+        # build with more FP64 work than its kernels need (frac_census can exceed 1)
         roofline = {
-            "bound": "fp64", "kernel": "table_kernel<photonuclear | pair | bremsstrahlung | "
-                                       "ionisation> (one chained build)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "frac_executed": (executed / per_gpu_s / c.fp64_peak) if executed else None,
+            "bound": "fp64", "kernel": "table_terms_kernel<photonuclear | pair_production | "
+                                       "bremsstrahlung+ionisation> + table_sum_kernel (one chained "
+                                       "build, flat form)",
+            "achieved": (executed * 2 / per_gpu_s / 1e12) if executed else achieved,
+            "peak": peak, "unit": "TFLOP/s",
+            "frac": frac_executed if frac_executed is not None else achieved / peak,
+            "frac_executed": frac_executed,
+            "frac_census": achieved / peak, "achieved_census": achieved,
             "traffic": c.profile.get("table_build_dram_bytes"),
+            "traffic_note": "the node terms make one round trip through a workspace (16 B per node "
+                            "and process written and read back: 1.28 GB per build, ~5 % of HBM "
+                            "bandwidth over the build) so that no CTA ever waits on a row's "
+                            "serial-order sum; input + output are 0.72 MB",
             "peak_source": "measured live: noa_dcs_fp64_probe (16 independent DFMA chains/thread), "
                            f"{c.fp64_peak / 1e12:.2f} T DFMA/s; MEASURED_PEAKS.json has no FP64 entry",
             "algorithmic": {"fp64_pipe_instr_per_build": algo,
                             "in_range_node_evals": inr, "node_evals": EVALS_PER_BUILD,
                             "per_eval": ALGO_INSTR, "per_node_overhead": NODE_OVERHEAD_INSTR,
-                            "bytes_per_build": 8 * N_K + 64 * N_K},
+                            "bytes_per_build": 8 * N_K + 64 * N_K,
+                            "workspace_bytes_per_build": 2 * 16 * EVALS_PER_BUILD},
             "executed": {"fp64_instr_per_build": executed,
                          "source": c.profile.get("source"), "commit": c.profile.get("commit")},
             "kernel_ms": ms_per_build, "gpus": c.world,

@@ -259,10 +259,14 @@ namespace noa::pms::dcs::cuda {
         if (K.numel() == 0) return result;
         const c10::cuda::CUDAGuard guard(K.device());
         double *base = result.data_ptr<double>();
-        check_rc(noa_dcs_table_f64(0xFu, K.data_ptr<double>(), K.numel(), xlow, min_points, el.A,
-                                   el.I, el.Z, mass, base, base + 4 * K.numel(),
-                                   current_stream(K)),
-                 "noa_dcs_table_f64");
+        // flat form: the node terms go through a workspace (16 B per node and process) taken from
+        // the stream-ordered caching allocator for the duration of the launches
+        const int64_t need = noa_dcs_table_workspace_doubles(K.numel(), min_points);
+        const auto workspace = torch::empty({need}, K.options());
+        check_rc(noa_dcs_table_ws_f64(0xFu, K.data_ptr<double>(), K.numel(), xlow, min_points, el.A,
+                                      el.I, el.Z, mass, base, base + 4 * K.numel(),
+                                      workspace.data_ptr<double>(), need, current_stream(K)),
+                 "noa_dcs_table_ws_f64");
         return result;
     }
 

@@ -28,7 +28,8 @@ def main(path, commit):
     idx = {h: i for i, h in enumerate(hdr)}
     out = {"source": f"ncu --set full of tools/profile_kernels.py ({path})", "commit": commit,
            "note": "instr per eval = warp instructions per warp of 32 evaluations (full warps); "
-                   "table_build_* = sums over the four chained table kernels of one config-4 build; "
+                   "table_build_* = sums over the chained kernels of one config-4 build (row "
+                   "parameters, three terms kernels, summation); "
                    "fp64 instructions counted as sm__inst_executed_pipe_fp64.sum x 32 lanes"}
     table = {"fp64": 0.0, "inst": 0.0, "dram": 0.0, "ms": {}}
     for d in data:
@@ -51,6 +52,21 @@ def main(path, commit):
             out[f"{pr}_dram_bytes_per_launch"] = dram
             out[f"{pr}_fp64_pipe_pct"] = float(
                 d[idx["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]])
+        elif "table_terms_kernel<" in name or "table_sum_kernel" in name or "table_rowpar" in name:
+            if "table_terms_kernel<" in name:
+                m = name.split("table_terms_kernel<")[1].split(">")[0].strip().replace("(int)", "")
+                key = {"0": "bremsstrahlung", "1": "pair_production", "2": "photonuclear",
+                       "3": "ionisation", "4": "bremsstrahlung+ionisation"}.get(m, m)
+            else:
+                key = "summation" if "table_sum_kernel" in name else "row_parameters"
+            table["fp64"] += fp64 * 32
+            table["inst"] += inst * 32
+            table["dram"] += dram
+            table["ms"][key] = ms
+            out[f"table_{key}_fp64_pipe_pct"] = float(
+                d[idx["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]])
+            out[f"table_{key}_dram_bytes"] = dram
+            out[f"table_{key}_fp64_instr_executed"] = fp64 * 32
         elif "table_kernel<" in name:
             m = name.split("table_kernel<")[1].split(",")[0].strip().replace("(unsigned int)", "")
             table["fp64"] += fp64 * 32
@@ -65,6 +81,7 @@ def main(path, commit):
     out["table_build_dram_bytes"] = table["dram"]
     out["table_build_kernel_ms_under_ncu"] = table["ms"]
     out["table_build_algorithmic_bytes"] = 8 * 10000 + 64 * 10000
+    out["table_build_workspace_bytes"] = 2 * 16 * 4 * NODES     # node terms written and read back
     print(json.dumps(out, indent=1))
 
 
