@@ -66,11 +66,12 @@ static int run_rank(int rank, int sock) {
     CHECK(cudaMalloc(&d_K_local, K_local.size() * sizeof(double)));
     CHECK(cudaMalloc(&d_K, n * sizeof(double)));
     CHECK(cudaMalloc(&d_ref, table_doubles * sizeof(double)));
-    const size_t sync_words = 8 + 4 * K_local.size();     // see noa_dcs_table_exchange_f64
+    const size_t sync_words = 8;                          // see noa_dcs_table_exchange_f64
     CHECK(cudaMalloc(&d_sync, sync_words * sizeof(uint32_t)));
     CHECK(cudaMemset(d_sync, 0, sync_words * sizeof(uint32_t)));
-    // optional: lets the build cut rows into pieces when a rank has few waves of heavy rows
-    const int64_t scratch_doubles = 4 * (int64_t) K_local.size() * 6 * ((min_points + 5) / 6);
+    // workspace of the flat build: 16 B per node and process of the local rows
+    const int64_t scratch_doubles =
+            noa_dcs_table_workspace_doubles((int64_t) K_local.size(), min_points);
     double *d_scratch = nullptr;
     CHECK(cudaMalloc(&d_scratch, scratch_doubles * sizeof(double)));
     CHECK(cudaMemcpy(d_K_local, K_local.data(), K_local.size() * sizeof(double),

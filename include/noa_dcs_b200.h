@@ -160,18 +160,17 @@ int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int6
  * row of the build is stored and fenced, the build writes `epoch` into slot `my_peer` of every
  * peer's flag array (peer_flags[j] = peer j's array of n_peers 32-bit words, mapped here like the
  * tables) and returns only when all n_peers slots of its own array have reached `epoch`, i.e. when
- * every peer's rows have landed in this GPU's table.  Persistent CTAs pull rows from a device-side
- * queue, store finished values to all peers as they go and pay one system-scope fence each; work
- * enqueued after the call on `stream` sees the complete table.  `epoch` must increase by one per
+ * every peer's rows have landed in this GPU's table; work enqueued after the call on `stream` sees
+ * the complete table.  `epoch` must increase by one per
  * call on all ranks (flags start at 0, first epoch 1); callers alternate between two destination
  * tables so a fast rank never overwrites rows a slow rank is still reading.
- * `sync` = 8 + 4 * n_local zero-initialised 32-bit words on this device {CTA counter, timeout
- * count, 2 reserved, 4 row queues, then one arrival word per (process, local row)}.
- * `scratch` (optional, may be NULL) = workspace of noa_dcs_table_ws_f64 for the LOCAL rows
- * (scratch_doubles >= noa_dcs_table_workspace_doubles(n_local, min_points)): the build then runs
- * in the flat form, whose summation kernel stores the finished rows to every peer and whose last
- * CTA runs the flag exchange -- one rank of eight holds 1 250 rows per process on config 4, too few
- * waves for the row-per-CTA forms.  Without it: persistent CTAs pulling rows from the queues.  A peer that does not arrive within `timeout_seconds` of wall-clock time
+ * `sync` = EIGHT zero-initialised 32-bit words on this device {CTA counter, timeout count, 6
+ * reserved}.
+ * `scratch` = workspace of noa_dcs_table_ws_f64 for the LOCAL rows, REQUIRED
+ * (scratch_doubles >= noa_dcs_table_workspace_doubles(n_local, min_points), else
+ * NOA_DCS_EINVAL): the exchange build is the flat form -- terms kernels over the local (row, node)
+ * space, then the summation kernel, which stores every finished row into all n_peers tables and
+ * whose last CTA runs the flag exchange.  A peer that does not arrive within `timeout_seconds` of wall-clock time
  * (<= 0: NOA_DCS_DEFAULT_EXCHANGE_TIMEOUT_S) is FATAL: the timeout count is bumped and the kernel
  * traps, so the stream reports a launch failure instead of handing back a partial table.
  */

@@ -290,15 +290,14 @@ static int vmap_all_impl(const double *K, const double *q, double *out, int64_t 
 // ---- table launches ---------------------------------------------------------------------------
 using TableKernel = void (*)(const double *, int64_t, TableOut, TablePlan, Params);
 
-template <bool PERSISTENT>
 static TableKernel table_kernel_for(unsigned mask) {
     switch (mask) {
-        case 1u: return table_kernel<1u, PERSISTENT>;
-        case 2u: return table_kernel<2u, PERSISTENT>;
-        case 4u: return table_kernel<4u, PERSISTENT>;
-        case 8u: return table_kernel<8u, PERSISTENT>;
+        case 1u: return table_kernel<1u>;
+        case 2u: return table_kernel<2u>;
+        case 4u: return table_kernel<4u>;
+        case 8u: return table_kernel<8u>;
     }
-    return table_kernel<15u, PERSISTENT>;
+    return table_kernel<15u>;
 }
 
 static int rows_per_item(int process) {
@@ -307,12 +306,12 @@ static int rows_per_item(int process) {
                    : TableCfg<1>::R;
 }
 
-// How a multi-process build is launched: one kernel per process, chained with programmatic
-// dependent launch (each with the register budget its integrand wants), or one combined kernel.
-// Measured on config 4 (profiles/r02_table_variants.jsonl): 10^4 rows per process 4.49 ms split
-// against 4.63 combined, but 1 250 rows per process (one rank of eight) 0.645 split against 0.608
-// combined -- with few waves of rows the boundaries between four kernels cost more than the
-// combined kernel's one-size register budget.  Hence: split from kTableSplitRows rows on.
+// How a multi-process build of the row-per-CTA form is launched: one kernel per process, chained
+// with programmatic dependent launch (each with the register budget its integrand wants), or one
+// combined kernel.  Measured on config 4: 10^4 rows per process 4.31 ms split against 4.42
+// combined; at 1 250 rows per process the two are within 1 % (0.592 / 0.590 ms,
+// profiles/r02_flat_table_study.md) and the combined kernel is one launch.  Hence: split from
+// kTableSplitRows rows on.
 // NOA_DCS_TABLE_LAUNCH=split|combined (read once, not a run-time switch) forces one form so both
 // stay measurable.
 constexpr int64_t kTableSplitRows = 4096;
@@ -416,15 +415,23 @@ static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, d
     FlatSum fs{};
     fs.quadrature_only = fp.quadrature_only;
     fs.xlow = xlow;
-    bool launched = false;
+    // Launch order: terms of photonuclear, pair production, bremsstrahlung + ionisation, then ONE
+    // summation kernel over all rows.  (Adding the heavy rows up beside the last terms kernel
+    // instead -- memory-bound next to FP64-bound -- was measured and lost: 4.22 against 4.16 ms, and
+    // 0.603 against 0.565 ms on a 1/8 share; profiles/r02_flat_table_study.md.)
+    int n_slots = 0;
     for (int i = 0; i < 4; i++) {
         const int pr = heavy_first[i];
         if (!((process_mask >> pr) & 1u)) continue;
-        const int slot = fs.n_slots++;
+        fs.process[n_slots] = pr;
+        fs.out_row[n_slots] = pr;
+        fs.terms[n_slots] = terms + (int64_t) n_slots * nK * nodes;
+        n_slots++;
+    }
+    bool launched = false;
+    for (int slot = 0; slot < n_slots; slot++) {
+        const int pr = fs.process[slot];
         double2 *t = terms + (int64_t) slot * nK * nodes;
-        fs.process[slot] = pr;
-        fs.out_row[slot] = pr;
-        fs.terms[slot] = t;
         // bremsstrahlung and ionisation together go through one fused launch (heavy_first ends
         // with bremsstrahlung, ionisation: their slots are adjacent)
         const bool both_light = (process_mask & 9u) == 9u;
@@ -442,7 +449,9 @@ static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, d
         if (rc) return rc;
         launched = true;
     }
-    const int64_t chains = nK * fs.n_slots;
+    fs.first_slot = 0;
+    fs.n_slots = n_slots;
+    const int64_t chains = nK * n_slots;
     const unsigned grid = (unsigned) ((chains + kSumWarps - 1) / kSumWarps);
     out.total_ctas = grid;
     return launch_chained(table_sum_kernel, grid, 32u * kSumWarps, true, s, K, nK,
@@ -464,6 +473,9 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
     }
     if (!K) return NOA_DCS_EINVAL;
     if (nK > 0x3fffffffLL) return NOA_DCS_ERANGE;
+    const bool flat = !single_row && opt.workspace &&
+                      opt.workspace_doubles >= table_workspace_doubles(nK, min_points);
+    if (exchange && !flat) return NOA_DCS_EINVAL;   // the exchange form is the flat form
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
@@ -477,9 +489,7 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
         if (rc) return rc;
     }
 
-    if (!single_row && opt.workspace &&
-        opt.workspace_doubles >= table_workspace_doubles(nK, min_points))
-        return table_flat_impl(process_mask, K, nK, xlow, min_points, p, out, s, opt);
+    if (flat) return table_flat_impl(process_mask, K, nK, xlow, min_points, p, out, s, opt);
 
     static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
                                        NOA_DCS_BREMSSTRAHLUNG, NOA_DCS_IONISATION};
@@ -507,7 +517,7 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
     if (all.n_slots == 1 || !table_launch_split(nK)) {
         plans[0] = all;
         const unsigned mask = all.n_slots == 1 ? (1u << all.process[0]) : 15u;
-        kernels[0] = exchange ? table_kernel_for<true>(mask) : table_kernel_for<false>(mask);
+        kernels[0] = table_kernel_for(mask);
         n_launch = 1;
     } else {
         for (int i = 0; i < all.n_slots; i++) {
@@ -516,28 +526,16 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
             one.process[0] = all.process[i];
             one.out_row[0] = all.out_row[i];
             one.items[0] = all.items[i];
-            one.queue = i;
             plans[i] = one;
-            const unsigned mask = 1u << all.process[i];
-            kernels[i] = exchange ? table_kernel_for<true>(mask) : table_kernel_for<false>(mask);
+            kernels[i] = table_kernel_for(1u << all.process[i]);
         }
         n_launch = all.n_slots;
     }
-    uint32_t total_ctas = 0;
     for (int i = 0; i < n_launch; i++) {
         uint64_t items = 0;
         for (int sl = 0; sl < plans[i].n_slots; sl++) items += plans[i].items[sl];
-        if (exchange) {
-            int per_sm = 0;
-            rc = blocks_per_sm((const void *) kernels[i], per_sm);
-            if (rc) return rc;
-            const uint64_t cap = (uint64_t) info.sm_count * per_sm;
-            if (items > cap) items = cap;
-        }
         grids[i] = (unsigned) items;
-        total_ctas += grids[i];
     }
-    out.total_ctas = total_ctas;
     for (int i = 0; i < n_launch; i++) {
         rc = launch_table(kernels[i], grids[i], i > 0, s, K, nK, out, plans[i], p);
         if (rc) return rc;

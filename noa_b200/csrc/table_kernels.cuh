@@ -21,13 +21,14 @@
 //
 // The row body is instantiated per process (`table_item<PROCESS>`, out of line): every integrand
 // gets its own register allocation instead of one 64-register body that holds all four (636 B of
-// spills, 145 MB of local-memory traffic per build in round 1).  Two launch shapes use it:
-//   table_kernel<MASK, false>   one CTA per item (grid = number of items)
-//   table_kernel<MASK, true>    persistent CTAs popping items from a device-side queue; used by
-//                               the multi-GPU exchange, where each CTA pays ONE system-scope fence
-// MASK = 15 is the combined kernel (all processes, register budget of the largest); single-bit
+// spills, 145 MB of local-memory traffic per build in round 1).  table_kernel<MASK>: one CTA per
+// item; MASK = 15 is the combined kernel (all processes, register budget of the largest), single-bit
 // masks are per-process kernels with their own launch bounds, chained with programmatic dependent
 // launch so the tail of one process overlaps the head of the next.
+//
+// This row-per-CTA form serves the calls that bring no workspace (noa_dcs_table_f64,
+// noa_dcs_vmap_integral*_f64, noa_dcs_table_scatter_f64).  Builds with a workspace -- the Python /
+// C++ `tables`, the multi-GPU exchange -- run the flat form further down.
 #pragma once
 
 #include <climits>
@@ -59,7 +60,7 @@ struct TableOut {
     double *del[NOA_DCS_MAX_PEERS];
     double *cel[NOA_DCS_MAX_PEERS];
     // exchange form (noa_dcs_table_exchange_f64): flags[j] = peer j's array of n_peers epoch words;
-    // sync = this GPU's words {CTA counter, timeouts, -, -, queue 0..3}; flags[0] == nullptr otherwise
+    // sync = this GPU's words {CTA counter, timeouts, 6 reserved}; flags[0] == nullptr otherwise
     uint32_t *flags[NOA_DCS_MAX_PEERS];
     uint32_t *sync;
     uint32_t epoch;
@@ -73,7 +74,6 @@ struct TablePlan {
     int32_t out_row[4];       // output row of process p (p for full tables, 0 for a single column)
     uint32_t items[4];        // items of slot s = ceil(nK / R(process))
     uint32_t cells;           // ceil(min_points / 6)
-    int32_t queue;            // persistent form: index of this launch's queue word (sync[4 + queue])
     double xlow;
     // generalised form (noa_dcs_vmap_integral_mode_f64; PUMAS's compute_dcs_integral shape,
     // pumas.c:10901-10955): upper bound ln(K xhigh) instead of ln K, the second chain's integrand
@@ -91,7 +91,6 @@ struct TableShared {
     int64_t row_at[kTableMaxRows];          // destination index of the row, -1 = no such row
     int32_t row_quad[kTableMaxRows];        // 1 = quadrature, 0 = closed form / no row
     int32_t lo, hi;                         // index range of the non-zero terms of the pass
-    uint32_t next[2];                       // persistent form: the CTA's next item
 };
 
 // ---- programmatic dependent launch ------------------------------------------------------------
@@ -125,8 +124,6 @@ __device__ __forceinline__ void table_exchange_tail(const TableOut &out) {
     if (arrived != out.total_ctas - 1) return;
     // re-armed for the next build on this stream
     out.sync[0] = 0;
-#pragma unroll
-    for (int w = 4; w < 8; w++) out.sync[w] = 0;
     __threadfence_system();
     for (int j = 0; j < out.n_peers; j++)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(out.flags[j] + out.me),
@@ -189,8 +186,7 @@ __device__ __forceinline__ void table_node_terms(uint32_t i, double k, double lb
 template <int PROCESS>
 __device__ __noinline__ void table_item(uint32_t item, int slot, const double *__restrict__ K,
                                         int64_t nK, const TableOut &out, const TablePlan &plan,
-                                        const Params &p, const glibm::Tab &T, TableShared &s,
-                                        uint32_t *queue, uint32_t *s_next) {
+                                        const Params &p, const glibm::Tab &T, TableShared &s) {
     constexpr int R = TableCfg<PROCESS>::R;
     constexpr int CH = 2 * R;
     static_assert(R <= kTableMaxRows && kTableTerms % R == 0, "rows per pass");
@@ -276,16 +272,9 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
                     s.lo = INT_MAX;
                     s.hi = -1;
                 }
-            } else if (tid == 64 && queue != nullptr && base + per_pass >= total) {
-                // persistent form: this idle lane pops the CTA's next item while the chains run --
-                // late enough that a heavy row in flight never sits on an item another CTA could
-                // have started, early enough that the atomic's round trip is hidden
-                *s_next = atomicAdd(queue, 1u);
             }
             __syncthreads();
         }
-    } else if (queue != nullptr && tid == 64) {
-        *s_next = atomicAdd(queue, 1u);
     }
 
     if (tid < CH && s.row_at[my_row] >= 0) {
@@ -311,34 +300,33 @@ struct TableMinBlocks {
                                                  : NOA_MINB_TABLE_LIGHT;
 };
 
-template <unsigned MASK, bool PERSISTENT>
+template <unsigned MASK>
 __device__ __forceinline__ void table_dispatch(uint32_t b, const double *__restrict__ K, int64_t nK,
                                                const TableOut &out, const TablePlan &plan,
-                                               const Params &p, const glibm::Tab &T, TableShared &s,
-                                               uint32_t *queue, uint32_t *s_next) {
+                                               const Params &p, const glibm::Tab &T, TableShared &s) {
     int slot = 0;
     while (slot < plan.n_slots - 1 && b >= plan.items[slot]) b -= plan.items[slot++];
     switch (plan.process[slot]) {      // CTA-uniform
         case 0:
-            if (MASK & 1u) table_item<0>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            if (MASK & 1u) table_item<0>(b, slot, K, nK, out, plan, p, T, s);
             break;
         case 1:
             if (MASK & 2u) {
-                table_item<1>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+                table_item<1>(b, slot, K, nK, out, plan, p, T, s);
             }
             break;
         case 2:
             if (MASK & 4u) {
-                table_item<2>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+                table_item<2>(b, slot, K, nK, out, plan, p, T, s);
             }
             break;
         default:
-            if (MASK & 8u) table_item<3>(b, slot, K, nK, out, plan, p, T, s, queue, s_next);
+            if (MASK & 8u) table_item<3>(b, slot, K, nK, out, plan, p, T, s);
             break;
     }
 }
 
-template <unsigned MASK, bool PERSISTENT>
+template <unsigned MASK>
 __global__ void __launch_bounds__(kThreads, TableMinBlocks<MASK>::value)
 table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ TableOut out,
              const __grid_constant__ TablePlan plan, const __grid_constant__ Params p) {
@@ -350,25 +338,11 @@ table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ T
     // the next launch of the build (another process: disjoint rows) may start filling SMs as
     // soon as every CTA of this one is resident or done
     pdl_release_dependents();
-    if (PERSISTENT) {
-        uint32_t total = 0;
-        for (int i = 0; i < plan.n_slots; i++) total += plan.items[i];
-        uint32_t *queue = out.sync + 4 + plan.queue;
-        if (threadIdx.x == 64) s.next[0] = atomicAdd(queue, 1u);
-        for (int cur = 0;; cur ^= 1) {
-            __syncthreads();                   // s.next[cur] written; shared buffers free again
-            const uint32_t b = s.next[cur];
-            if (b >= total) break;
-            table_dispatch<MASK, true>(b, K, nK, out, plan, p, T, s, queue, &s.next[cur ^ 1]);
-        }
-    } else {
-        table_dispatch<MASK, false>(blockIdx.x, K, nK, out, plan, p, T, s, nullptr, nullptr);
-        // scatter form without flags: the writer lanes fence their own remote stores
-        if (out.n_peers > 1 && out.flags[0] == nullptr && threadIdx.x < 32) __threadfence_system();
-    }
+    table_dispatch<MASK>(blockIdx.x, K, nK, out, plan, p, T, s);
+    // scatter form: the writer lanes fence their own remote stores
+    if (out.n_peers > 1 && threadIdx.x < 32) __threadfence_system();
     // completion order along the chain: this kernel does not retire before its predecessor has
     if (threadIdx.x == 0) pdl_wait_prerequisites();
-    if (out.flags[0] != nullptr) table_exchange_tail(out);
 }
 
 // bremsstrahlung (td, tc) and, if `ion`, ionisation (ud, uc) terms of one node
@@ -512,7 +486,7 @@ table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__re
 }
 
 struct FlatSum {
-    int32_t n_slots;
+    int32_t first_slot, n_slots;    // the slots this launch adds up
     int32_t process[4];
     int32_t out_row[4];             // output row of slot s
     const double2 *terms[4];        // [nK][nodes]
@@ -546,13 +520,14 @@ table_sum_kernel(const double *__restrict__ K, int64_t nK, uint32_t nodes,
     __shared__ glibm::Tables s_tables;
     __shared__ double2 s_ring[kSumWarps][2][kSumStage];
     const glibm::Tab T = stage_tables(s_tables);     // for the closed-form rows
-    pdl_wait_prerequisites();       // every terms kernel of the build has completed
+    pdl_wait_prerequisites();       // the terms kernels of the build have completed
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t w = threadIdx.x >> 5;
-    const int64_t chain = (int64_t) blockIdx.x * kSumWarps + w;
-    if (chain < nK * fs.n_slots) {
-        const int slot = (int) (chain / nK);
-        const int64_t row = nK - 1 - (chain - (int64_t) slot * nK);
+    const int64_t chains = nK * fs.n_slots;
+    for (int64_t chain = (int64_t) blockIdx.x * kSumWarps + w; chain < chains;
+         chain += (int64_t) gridDim.x * kSumWarps) {
+        const int slot = fs.first_slot + (int) (chain / nK);
+        const int64_t row = nK - 1 - chain % nK;
         const double k = K[row];
         const bool closed = fs.process[slot] == 3 && k <= p.i_kthr && !fs.quadrature_only;
         double acc = 0.;

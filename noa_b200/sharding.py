@@ -210,9 +210,8 @@ class PeerTableBuilder(_HostTables):
         self._del = [(vp * world)(*[p + b * per_table * 8 for p in ptrs]) for b in range(2)]
         self._cel = [(vp * world)(*[p + b * per_table * 8 + half for p in ptrs]) for b in range(2)]
         self._flags = (vp * world)(*[p + 2 * per_table * 8 for p in ptrs])
-        # {CTA counter, timeouts, 2 reserved, 4 row queues, a hand-over word per (process, local row)}
-        # (noa_dcs_table_exchange_f64: `sync`)
-        self.done = torch.zeros(8 + 4 * self.n_local, dtype=torch.int32, device=K.device)
+        # {CTA counter, timeouts, 6 reserved} (noa_dcs_table_exchange_f64: `sync`)
+        self.done = torch.zeros(8, dtype=torch.int32, device=K.device)
         # workspace of the flat form (node terms), sized at the first build
         self.scratch = None
         self.epoch = 0

@@ -17,9 +17,9 @@ for W in (1, 2, 4, 8):
     n = Kl.numel()
     table = torch.zeros((2, 4, n), dtype=torch.float64, device="cuda")
     flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    sync = torch.zeros(8 + 4 * n, dtype=torch.int32, device="cuda")
+    sync = torch.zeros(8, dtype=torch.int32, device="cuda")
     dl = (vp * 1)(table.data_ptr()); cl = (vp * 1)(table.data_ptr() + 4 * n * 8); fl = (vp * 1)(flags.data_ptr())
-    scratch = torch.empty(2 * n + 8 * n * 1002, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(int(lib.noa_dcs_table_workspace_doubles(n, 1000)), dtype=torch.float64, device="cuda")
     epoch = [0]
     def build():
         epoch[0] += 1
