@@ -329,6 +329,89 @@ def test_table_odd_node_counts(port):
             assert_parity(result, want, (mp, pr.name))
 
 
+@pytest.mark.parametrize("min_points", [1, 7, 31, 180, 257, 1000, 1537, 4000])
+def test_flat_tables_against_oracle_and_rows_form(port, min_points):
+    """The workspace ("flat") form of the table build -- 32-node units popped by warps, terms
+    through the workspace, summation kernel -- against the oracle's recoil integrals and against
+    the row-per-CTA form, at node counts below / at / above a unit, a summation stage (256) and a
+    shared-memory pass (1536), on a ragged number of rows that spans the ionisation closed-form
+    threshold and the kinematic thresholds of pair production and photonuclear."""
+    K = grids.table_energies(37, -2.0, 6.0)
+    Kd = dev(K)
+    d_flat, c_flat = dcs.cuda.tables(Kd, 0.05, ELEMENTS["rock"], MUON_MASS, min_points, flat=True)
+    d_rows, c_rows = dcs.cuda.tables(Kd, 0.05, ELEMENTS["rock"], MUON_MASS, min_points, flat=False)
+    assert torch.equal(d_flat, d_rows) and torch.equal(c_flat, c_rows)
+    for pr in dcs.PROCESSES:
+        for ig, got in ((0, d_flat), (1, c_flat)):
+            want = port.vmap_integral(pr.index, ig, K, 0.05, min_points, ELEMENTS["rock"],
+                                      MUON_MASS, threads=8)
+            assert_parity(got[pr.index], want, (min_points, pr.name, ig))
+
+
+@pytest.mark.parametrize("mask", [1, 2, 4, 8, 9, 6, 10, 7, 14])
+def test_flat_tables_process_subsets(mask):
+    """Every way the flat build groups its launches (bremsstrahlung + ionisation fused or alone,
+    heavy processes present or not): requested rows equal the full build's, the others are zero --
+    also when the output held something else before."""
+    K = dev(grids.table_energies(203, -2.0, 6.0))
+    full_d, full_c = dcs.cuda.tables(K, 0.05, ELEMENTS["Pb"], MUON_MASS, 180, flat=True)
+    procs = tuple(pr for pr in dcs.PROCESSES if (mask >> pr.index) & 1)
+    out = (torch.full((4, 203), 7.0, dtype=torch.float64, device="cuda"),
+           torch.full((4, 203), -3.0, dtype=torch.float64, device="cuda"))
+    d, c = dcs.cuda.tables(K, 0.05, ELEMENTS["Pb"], MUON_MASS, 180, processes=procs, out=out,
+                           flat=True)
+    for pr in dcs.PROCESSES:
+        if (mask >> pr.index) & 1:
+            assert torch.equal(d[pr.index], full_d[pr.index]), (mask, pr.name)
+            assert torch.equal(c[pr.index], full_c[pr.index]), (mask, pr.name)
+        else:
+            assert float(d[pr.index].abs().sum()) == 0.0 and float(c[pr.index].abs().sum()) == 0.0
+
+
+def test_table_workspace_contract():
+    """C ABI: noa_dcs_table_workspace_doubles sizes the workspace; a NULL or short workspace makes
+    noa_dcs_table_ws_f64 fall back to the row-per-CTA launches (same bits); the exchange form
+    refuses to run without one."""
+    import ctypes
+    from noa_b200 import _lib
+    lib = _lib.require_device()
+    vp = ctypes.c_void_p
+    n, mp = 100, 180
+    need = int(lib.noa_dcs_table_workspace_doubles(n, mp))
+    assert need >= 8 * n * 180 and lib.noa_dcs_table_workspace_doubles(0, mp) == 0
+    K = dev(grids.table_energies(n, -2.0, 6.0))
+    ws = torch.empty(need, dtype=torch.float64, device="cuda")
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    tabs = []
+    for doubles in (need, need - 1, 0):
+        t = torch.full((2, 4, n), 5.0, dtype=torch.float64, device="cuda")
+        _lib.check(lib.noa_dcs_table_ws_f64(15, vp(K.data_ptr()), n, 0.05, mp, 22., 0.1364e-6, 11,
+                                            MUON_MASS, vp(t.data_ptr()),
+                                            vp(t.data_ptr() + 4 * n * 8),
+                                            vp(ws.data_ptr()) if doubles else None, doubles, stream))
+        tabs.append(t)
+    torch.cuda.synchronize()
+    assert torch.equal(tabs[0], tabs[1]) and torch.equal(tabs[0], tabs[2])
+    # exchange form, this GPU as its only peer, no scratch: invalid argument, nothing launched
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    sync = torch.zeros(8, dtype=torch.int32, device="cuda")
+    t = tabs[0]
+    dl, cl, fl = (vp * 1)(t.data_ptr()), (vp * 1)(t.data_ptr() + 4 * n * 8), (vp * 1)(flags.data_ptr())
+    rc = lib.noa_dcs_table_exchange_f64(15, vp(K.data_ptr()), n, 0.05, mp, 22., 0.1364e-6, 11,
+                                        MUON_MASS, 1, 0, dl, cl, fl, vp(sync.data_ptr()), None, 0,
+                                        1, n, 0, 1, 5.0, stream)
+    assert rc == -1      # NOA_DCS_EINVAL
+    # ... and with one: the same table
+    t2 = torch.zeros((2, 4, n), dtype=torch.float64, device="cuda")
+    dl2, cl2 = (vp * 1)(t2.data_ptr()), (vp * 1)(t2.data_ptr() + 4 * n * 8)
+    _lib.check(lib.noa_dcs_table_exchange_f64(15, vp(K.data_ptr()), n, 0.05, mp, 22., 0.1364e-6,
+                                              11, MUON_MASS, 1, 0, dl2, cl2, fl,
+                                              vp(sync.data_ptr()), vp(ws.data_ptr()), need, 1, n,
+                                              0, 1, 5.0, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(t2, tabs[0])
+
+
 def test_full_size_properties():
     """BASELINE config 2 size (2^22 pairs): size-independent checks -- determinism, agreement of a
     strided sample with the oracle is covered above; here: repeatability, slice consistency
