@@ -192,7 +192,7 @@ static int device_info(DeviceInfo &info) {
 // Resident CTAs per SM of a kernel at kThreads threads.  The occupancy query costs a few
 // microseconds -- a quarter of a 10^4-pair call -- so the answer is kept per kernel (all devices of
 // a box are the same part).
-static int blocks_per_sm(const void *kernel, int &per_sm) {
+static int blocks_per_sm(const void *kernel, int &per_sm, int threads = kThreads) {
     static std::mutex mu;
     static const void *keys[64];
     static int vals[64];
@@ -206,7 +206,7 @@ static int blocks_per_sm(const void *kernel, int &per_sm) {
             }
     }
     int v = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, 0);
     if (e != cudaSuccess) return (int) e;
     if (v < 1) v = 1;
     std::lock_guard<std::mutex> lock(mu);
@@ -384,11 +384,22 @@ template <int PROCESS>
 static int launch_terms(const double *K, int64_t nK, const double2 *rowpar, double2 *terms,
                         double2 *terms_b, uint32_t *queue, const FlatPlan &fp, const Params &p,
                         bool dependent, cudaStream_t s) {
-    int blocks = 0;
-    int rc = persistent_grid(table_terms_kernel<PROCESS>, nK * (int64_t) fp.cells * 6, blocks);
+    DeviceInfo info;
+    int rc = device_info(info);
     if (rc) return rc;
-    return launch_chained(table_terms_kernel<PROCESS>, (unsigned) blocks, kThreads, dependent, s, K,
-                          nK, rowpar, terms, terms_b, queue, fp, p);
+    int per_sm = 0;
+    rc = blocks_per_sm((const void *) table_terms_kernel<PROCESS>, per_sm, kFlatThreads);
+    if (rc) return rc;
+    // one warp per 32-node unit (FlatCfg::unit of them per pop), never more CTAs than fit at once
+    const int64_t warps = (nK * (int64_t) fp.cells * 6 + 31) / 32;
+    const int64_t need = (warps * 32 + kFlatThreads - 1) / kFlatThreads;
+    const int64_t cap = (int64_t) info.sm_count * (per_sm < 1 ? 1 : per_sm);
+    const unsigned blocks = (unsigned) (need < cap ? need : cap);
+    FlatPlan plan = fp;
+    plan.first_launch = dependent ? 0 : 1;
+    // every terms kernel is a dependent launch: the first one of table_rowpar_kernel
+    return launch_chained(table_terms_kernel<PROCESS>, blocks, (unsigned) kFlatThreads, true, s, K,
+                          nK, rowpar, terms, terms_b, queue, plan, p);
 }
 
 // The flat form of a table build (table_kernels.cuh): row parameters, one terms kernel per

@@ -397,6 +397,7 @@ struct FlatPlan {
     uint32_t cells;
     int32_t second_power;
     int32_t quadrature_only;
+    int32_t first_launch;           // terms kernel: 1 = the build's first (waits for rowpar)
     double xlow, xhigh;
 };
 
@@ -406,6 +407,7 @@ __global__ void table_rowpar_kernel(const double *__restrict__ K, int64_t nK,
                                     const __grid_constant__ FlatPlan plan,
                                     double2 *__restrict__ rowpar, uint32_t *__restrict__ queues) {
     __shared__ glibm::Tables s_tables;
+    pdl_release_dependents();       // the first terms kernel may get resident and stage its tables
     const glibm::Tab T = stage_tables(s_tables);
     const int64_t row = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (row < 4) queues[row] = 0;
@@ -428,8 +430,14 @@ struct FlatCfg {
     static constexpr unsigned mask = (PROCESS == 4) ? 9u : (1u << PROCESS);
 };
 
+#ifndef NOA_FLAT_THREADS
+#define NOA_FLAT_THREADS 256
+#endif
+constexpr int kFlatThreads = NOA_FLAT_THREADS;
+
 template <int PROCESS>
-__global__ void __launch_bounds__(kThreads, TableMinBlocks<FlatCfg<PROCESS>::mask>::value)
+__global__ void __launch_bounds__(kFlatThreads, TableMinBlocks<FlatCfg<PROCESS>::mask>::value *
+                                                        (kThreads / kFlatThreads))
 table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__restrict__ rowpar,
                    double2 *__restrict__ terms, double2 *__restrict__ terms_b,
                    uint32_t *__restrict__ queue, const __grid_constant__ FlatPlan fp,
@@ -439,8 +447,12 @@ table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__re
     if (threadIdx.x < 6)
         s_gl6[threadIdx.x] = make_double2(c_gl6_x[threadIdx.x], c_gl6_w[threadIdx.x]);
     const glibm::Tab T = stage_all(s_staged, p);
-    // the next launch of the build (another process: other terms) may fill SMs as they free up;
-    // rowpar was complete before the first terms kernel of the build started (stream order)
+    // The first terms kernel of a build is itself a dependent launch of table_rowpar_kernel (its
+    // CTAs stage their tables while that one runs): it waits here for the row parameters and
+    // the zeroed queues, and only then lets the next launch in -- so every later terms kernel
+    // starts after them too.  The later ones release at once: the next launch of the build
+    // (another process: other terms) may fill SMs as they free up.
+    if (fp.first_launch) pdl_wait_prerequisites();
     pdl_release_dependents();
     TablePlan plan{};
     plan.second_power = fp.second_power;
@@ -494,14 +506,20 @@ struct FlatSum {
     double xlow;
 };
 
+#ifndef NOA_SUM_WARPS
+#define NOA_SUM_WARPS 4
+#endif
+#ifndef NOA_SUM_STAGE
+#define NOA_SUM_STAGE 256
+#endif
 // One WARP per (process, row).  The row's terms stream through a private shared-memory ring
 // (cp.async, kSumStage nodes = 4 KB per stage, the next stage in flight while this one is added
 // up: enough bytes in flight per SM to keep HBM busy with a few thousand rows, and a row costs
 // its chain of additions -- 4.4 us at 1002 nodes -- plus one stage of latency however few rows
 // there are).  Lanes 0 and 1 own the two chains: res += f(x) h w[j] in node order
 // (numerics.hh:84-87).
-constexpr int kSumWarps = 4;
-constexpr uint32_t kSumStage = 256;
+constexpr int kSumWarps = NOA_SUM_WARPS;
+constexpr uint32_t kSumStage = NOA_SUM_STAGE;
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem)
