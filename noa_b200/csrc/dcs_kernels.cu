@@ -463,7 +463,24 @@ static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, d
     fs.first_slot = 0;
     fs.n_slots = n_slots;
     const int64_t chains = nK * n_slots;
-    const unsigned grid = (unsigned) ((chains + kSumWarps - 1) / kSumWarps);
+    int64_t ctas = (chains + kSumWarps - 1) / kSumWarps;
+    if (out.flags[0] != nullptr) {
+        // exchange form: every CTA ends on a system-scope fence that waits for its stores into the
+        // peers' tables (an NVLink round trip) while it still holds its share of the SM.  With one
+        // CTA per 4 rows that is paid once per wave of CTAs -- 5.6 waves on a half share: +24 us of
+        // a 2.1 ms build (tools/table_exchange_bench.py).  A grid that is resident at once, its
+        // warps striding over the rows, pays it once (2.130 -> 2.111 ms at 2 GPUs; without peers the
+        // capped grid is 0.4 % slower, so it is only used here).
+        DeviceInfo info;
+        rc = device_info(info);
+        if (rc) return rc;
+        int per_sm = 0;
+        rc = blocks_per_sm((const void *) table_sum_kernel, per_sm, 32 * kSumWarps);
+        if (rc) return rc;
+        const int64_t cap = (int64_t) info.sm_count * per_sm;
+        if (ctas > cap) ctas = cap;
+    }
+    const unsigned grid = (unsigned) ctas;
     out.total_ctas = grid;
     return launch_chained(table_sum_kernel, grid, 32u * kSumWarps, true, s, K, nK,
                           (uint32_t) nodes, fs, p, out);

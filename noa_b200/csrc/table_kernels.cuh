@@ -37,6 +37,15 @@
 
 namespace noa_b200 {
 
+// measurement-only switches (tools/table_exchange_bench.py builds variants with them; the product
+// build leaves both at 0): skip the stores into the peers' tables / do not wait for the peers' flags
+#ifndef NOA_XCHG_NO_REMOTE
+#define NOA_XCHG_NO_REMOTE 0
+#endif
+#ifndef NOA_XCHG_NO_WAIT
+#define NOA_XCHG_NO_WAIT 0
+#endif
+
 constexpr int kTableTerms = 1536;   // node terms staged per pass and integrand: 2 x 12 KB
 #ifndef NOA_TABLE_LIGHT_ROWS
 #define NOA_TABLE_LIGHT_ROWS 4
@@ -130,7 +139,7 @@ __device__ __forceinline__ void table_exchange_tail(const TableOut &out) {
                      "r"(out.epoch)
                      : "memory");
     const uint64_t t0 = global_timer_ns();
-    for (int j = 0; j < out.n_peers; j++) {
+    for (int j = 0; j < (NOA_XCHG_NO_WAIT ? 0 : out.n_peers); j++) {
         const uint32_t *slot = out.flags[out.me] + j;
         for (;;) {
             uint32_t seen;
@@ -586,7 +595,8 @@ table_sum_kernel(const double *__restrict__ K, int64_t nK, uint32_t nodes,
                                         : acc / (k + p.mass);
                 const int64_t at = (int64_t) fs.out_row[slot] * out.n_total + out.first_row +
                                    row * out.row_stride;
-                for (int j = 0; j < out.n_peers; j++) dst[j][at] = v;
+                for (int j = 0; j < out.n_peers; j++)
+                    if (!NOA_XCHG_NO_REMOTE || j == out.me) dst[j][at] = v;
                 // scatter form without flags: the writer lanes fence their own remote stores
                 if (out.n_peers > 1 && out.flags[0] == nullptr) __threadfence_system();
             }
