@@ -381,9 +381,8 @@ static int launch_chained(void (*kernel)(KArgs...), unsigned grid, unsigned bloc
 }
 
 template <int PROCESS>
-static int launch_terms(const double *K, int64_t nK, const double2 *rowpar, double2 *terms,
-                        double2 *terms_b, uint32_t *queue, const FlatPlan &fp, const Params &p,
-                        bool dependent, cudaStream_t s) {
+static int launch_terms(const double *K, int64_t nK, const double2 *rowpar, const FlatQueues &fq,
+                        const FlatPlan &fp, const Params &p, bool dependent, cudaStream_t s) {
     DeviceInfo info;
     int rc = device_info(info);
     if (rc) return rc;
@@ -399,7 +398,7 @@ static int launch_terms(const double *K, int64_t nK, const double2 *rowpar, doub
     plan.first_launch = dependent ? 0 : 1;
     // every terms kernel is a dependent launch: the first one of table_rowpar_kernel
     return launch_chained(table_terms_kernel<PROCESS>, blocks, (unsigned) kFlatThreads, true, s, K,
-                          nK, rowpar, terms, terms_b, queue, plan, p);
+                          nK, rowpar, fq, plan, p);
 }
 
 // The flat form of a table build (table_kernels.cuh): row parameters, one terms kernel per
@@ -439,24 +438,28 @@ static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, d
         fs.terms[n_slots] = terms + (int64_t) n_slots * nK * nodes;
         n_slots++;
     }
+    // bremsstrahlung and ionisation together go through one fused pass (heavy_first ends with
+    // bremsstrahlung, ionisation: their slots are adjacent)
+    const bool both_light = (process_mask & 9u) == 9u;
     bool launched = false;
     for (int slot = 0; slot < n_slots; slot++) {
         const int pr = fs.process[slot];
-        double2 *t = terms + (int64_t) slot * nK * nodes;
-        // bremsstrahlung and ionisation together go through one fused launch (heavy_first ends
-        // with bremsstrahlung, ionisation: their slots are adjacent)
-        const bool both_light = (process_mask & 9u) == 9u;
-        if (pr == NOA_DCS_IONISATION && both_light) continue;      // done with bremsstrahlung
+        FlatQueues fq{};
+        fq.terms_a = terms + (int64_t) slot * nK * nodes;
+        fq.queue_a = queues + slot;
         const bool dep = launched;
-        if (pr == NOA_DCS_BREMSSTRAHLUNG && both_light)
-            rc = launch_terms<4>(K, nK, rowpar, t, t + nK * nodes, queues + slot, fp, p, dep, s);
-        else
+        if (pr == NOA_DCS_IONISATION && both_light) continue;          // rides with bremsstrahlung
+        if (pr == NOA_DCS_BREMSSTRAHLUNG && both_light) {
+            fq.terms_b = fq.terms_a + nK * nodes;
+            rc = launch_terms<4>(K, nK, rowpar, fq, fp, p, dep, s);
+        } else {
             switch (pr) {
-                case 0: rc = launch_terms<0>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
-                case 1: rc = launch_terms<1>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
-                case 2: rc = launch_terms<2>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
-                default: rc = launch_terms<3>(K, nK, rowpar, t, nullptr, queues + slot, fp, p, dep, s); break;
+                case 0: rc = launch_terms<0>(K, nK, rowpar, fq, fp, p, dep, s); break;
+                case 1: rc = launch_terms<1>(K, nK, rowpar, fq, fp, p, dep, s); break;
+                case 2: rc = launch_terms<2>(K, nK, rowpar, fq, fp, p, dep, s); break;
+                default: rc = launch_terms<3>(K, nK, rowpar, fq, fp, p, dep, s); break;
             }
+        }
         if (rc) return rc;
         launched = true;
     }

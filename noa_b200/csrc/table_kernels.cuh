@@ -444,25 +444,15 @@ struct FlatCfg {
 #endif
 constexpr int kFlatThreads = NOA_FLAT_THREADS;
 
+// the units of one queue: PROCESS 0..3, or 4 = bremsstrahlung + ionisation fused
 template <int PROCESS>
-__global__ void __launch_bounds__(kFlatThreads, TableMinBlocks<FlatCfg<PROCESS>::mask>::value *
-                                                        (kThreads / kFlatThreads))
-table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__restrict__ rowpar,
-                   double2 *__restrict__ terms, double2 *__restrict__ terms_b,
-                   uint32_t *__restrict__ queue, const __grid_constant__ FlatPlan fp,
-                   const __grid_constant__ Params p) {
-    __shared__ StagedShared s_staged;
-    __shared__ double2 s_gl6[6];
-    if (threadIdx.x < 6)
-        s_gl6[threadIdx.x] = make_double2(c_gl6_x[threadIdx.x], c_gl6_w[threadIdx.x]);
-    const glibm::Tab T = stage_all(s_staged, p);
-    // The first terms kernel of a build is itself a dependent launch of table_rowpar_kernel (its
-    // CTAs stage their tables while that one runs): it waits here for the row parameters and
-    // the zeroed queues, and only then lets the next launch in -- so every later terms kernel
-    // starts after them too.  The later ones release at once: the next launch of the build
-    // (another process: other terms) may fill SMs as they free up.
-    if (fp.first_launch) pdl_wait_prerequisites();
-    pdl_release_dependents();
+__device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int64_t nK,
+                                               const double2 *__restrict__ rowpar,
+                                               double2 *__restrict__ terms,
+                                               double2 *__restrict__ terms_b,
+                                               uint32_t *__restrict__ queue, const FlatPlan &fp,
+                                               const Params &p, const glibm::Tab &T,
+                                               const double2 *gl6) {
     TablePlan plan{};
     plan.second_power = fp.second_power;
     const uint32_t nodes = fp.cells * 6u;
@@ -490,16 +480,46 @@ table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__re
             double td, tc;
             if (PROCESS == 4) {
                 double ud = 0., uc = 0.;
-                table_node_terms_light(i, k, lbh.x, lbh.y, !ion_closed, plan, p, T, s_gl6, td, tc,
-                                       ud, uc);
+                table_node_terms_light(i, k, lbh.x, lbh.y, !ion_closed, plan, p, T, gl6, td, tc, ud,
+                                       uc);
                 if (!ion_closed) terms_b[row * nodes + i] = make_double2(ud, uc);
             } else {
-                table_node_terms<(PROCESS == 4 ? 0 : PROCESS)>(i, k, lbh.x, lbh.y, plan, p, T,
-                                                                s_gl6, td, tc);
+                table_node_terms<(PROCESS == 4 ? 0 : PROCESS)>(i, k, lbh.x, lbh.y, plan, p, T, gl6,
+                                                                td, tc);
             }
             row_terms[i] = make_double2(td, tc);
         }
     }
+}
+
+// One launch = the units of one queue.  (Pair production and then, from a second queue, the
+// bremsstrahlung + ionisation units in ONE launch -- same register budget, the end of the pair
+// kernel filled with short units -- was measured and lost 0.4 % / 1.3 % on a full / a 1/8 share:
+// the combined kernel spills 148 B against 68; profiles/r02_flat_table_study.md.)
+struct FlatQueues {
+    double2 *terms_a, *terms_b;     // terms of the process; of ionisation in the fused pass
+    uint32_t *queue_a;
+};
+
+template <int PROCESS>
+__global__ void __launch_bounds__(kFlatThreads, TableMinBlocks<FlatCfg<PROCESS>::mask>::value *
+                                                        (kThreads / kFlatThreads))
+table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__restrict__ rowpar,
+                   const __grid_constant__ FlatQueues fq, const __grid_constant__ FlatPlan fp,
+                   const __grid_constant__ Params p) {
+    __shared__ StagedShared s_staged;
+    __shared__ double2 s_gl6[6];
+    if (threadIdx.x < 6)
+        s_gl6[threadIdx.x] = make_double2(c_gl6_x[threadIdx.x], c_gl6_w[threadIdx.x]);
+    const glibm::Tab T = stage_all(s_staged, p);
+    // The first terms kernel of a build is itself a dependent launch of table_rowpar_kernel (its
+    // CTAs stage their tables while that one runs): it waits here for the row parameters and
+    // the zeroed queues, and only then lets the next launch in -- so every later terms kernel
+    // starts after them too.  The later ones release at once: the next launch of the build
+    // (another process: other terms) may fill SMs as they free up.
+    if (fp.first_launch) pdl_wait_prerequisites();
+    pdl_release_dependents();
+    flat_run_units<PROCESS>(K, nK, rowpar, fq.terms_a, fq.terms_b, fq.queue_a, fp, p, T, s_gl6);
     // completion order along the chain: this kernel does not retire before its predecessor has,
     // so the summation kernel only has to wait for the last one
     __syncthreads();
