@@ -504,8 +504,10 @@ static int table_impl(unsigned process_mask, bool single_row, const double *K, i
     }
     if (!K) return NOA_DCS_EINVAL;
     if (nK > 0x3fffffffLL) return NOA_DCS_ERANGE;
+    // the flat form counts 32-node units in 32-bit queue words
     const bool flat = !single_row && opt.workspace &&
-                      opt.workspace_doubles >= table_workspace_doubles(nK, min_points);
+                      opt.workspace_doubles >= table_workspace_doubles(nK, min_points) &&
+                      nK * ((table_nodes(min_points) + 31) / 32) < 0xfff00000LL;
     if (exchange && !flat) return NOA_DCS_EINVAL;   // the exchange form is the flat form
     DeviceInfo info;
     int rc = device_info(info);
