@@ -354,6 +354,18 @@ table_kernel(const double *__restrict__ K, int64_t nK, const __grid_constant__ T
     if (threadIdx.x == 0) pdl_wait_prerequisites();
 }
 
+// the two terms of a node whose recoil energy q = exp(x) is already there
+template <int PROCESS>
+__device__ __forceinline__ void table_terms_at(double k, double q, double h, double w,
+                                               const TablePlan &plan, const Params &p,
+                                               const glibm::Tab &T, double &td, double &tc) {
+    const double fq = dcs_value<PROCESS, true>(k, q, p, T) * q;
+    td = fq * h * w;
+    double y = fq * q;
+    if (plan.second_power == 3) y *= q;
+    tc = y * h * w;
+}
+
 // bremsstrahlung (td, tc) and, if `ion`, ionisation (ud, uc) terms of one node
 __device__ __forceinline__ void table_node_terms_light(uint32_t i, double k, double lb, double h,
                                                        bool ion, const TablePlan &plan,
@@ -430,13 +442,16 @@ __global__ void table_rowpar_kernel(const double *__restrict__ K, int64_t nK,
 // Work unit = kFlatUnit x 32 consecutive nodes of one row, popped by a WARP from a device-side
 // queue (lane 0's atomic, one unit ahead so its latency is hidden): heaviest rows first, no
 // barrier anywhere, no static assignment whose period could lock onto the rows'.
-// PROCESS = 4: bremsstrahlung and ionisation of a node in one pass (one exp, two independent
-// integrands to interleave, one launch less -- a rank with few rows pays a wave of latency per
-// launch); `terms` then holds the bremsstrahlung terms and `terms_b` the ionisation ones.
+// PROCESS = 4: bremsstrahlung and ionisation of a node in one pass (one exp, one launch less);
+// `terms` then holds the bremsstrahlung terms and `terms_b` the ionisation ones.
+// PROCESS = 6: photonuclear with bremsstrahlung (`terms_b`) and ionisation (`terms_c`) riding on
+// its nodes: the two cheap processes are 4.5 % of the work but, launched on their own, one partial
+// wave of pure latency on a rank with few rows (45 us of a 565 us build on a 1/8 share); inside
+// the units of the heaviest kernel they cost their arithmetic and nothing else.
 template <int PROCESS>
 struct FlatCfg {
-    static constexpr uint32_t unit = (PROCESS == 1 || PROCESS == 2) ? 1u : 8u;
-    static constexpr unsigned mask = (PROCESS == 4) ? 9u : (1u << PROCESS);
+    static constexpr uint32_t unit = (PROCESS == 1 || PROCESS == 2 || PROCESS == 6) ? 1u : 8u;
+    static constexpr unsigned mask = (PROCESS == 4) ? 9u : (PROCESS == 6) ? 4u : (1u << PROCESS);
 };
 
 #ifndef NOA_FLAT_THREADS
@@ -450,6 +465,7 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
                                                const double2 *__restrict__ rowpar,
                                                double2 *__restrict__ terms,
                                                double2 *__restrict__ terms_b,
+                                               double2 *__restrict__ terms_c,
                                                uint32_t *__restrict__ queue, const FlatPlan &fp,
                                                const Params &p, const glibm::Tab &T,
                                                const double2 *gl6) {
@@ -478,13 +494,26 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
 #pragma unroll 1
         for (uint32_t i = first; i < min(nodes, first + span); i += 32u) {
             double td, tc;
-            if (PROCESS == 4) {
+            if (PROCESS == 6) {
+                // photonuclear, bremsstrahlung and ionisation of the node from one exp(x)
+                const uint32_t cell = i / 6u;
+                const double2 xw = gl6[i - cell * 6u];
+                const double q = glibm::exp(lbh.x + lbh.y * (cell + xw.x), T);
+                double ud, uc;
+                table_terms_at<0>(k, q, lbh.y, xw.y, plan, p, T, ud, uc);
+                terms_b[row * nodes + i] = make_double2(ud, uc);
+                if (!ion_closed) {
+                    table_terms_at<3>(k, q, lbh.y, xw.y, plan, p, T, ud, uc);
+                    terms_c[row * nodes + i] = make_double2(ud, uc);
+                }
+                table_terms_at<2>(k, q, lbh.y, xw.y, plan, p, T, td, tc);
+            } else if (PROCESS == 4) {
                 double ud = 0., uc = 0.;
                 table_node_terms_light(i, k, lbh.x, lbh.y, !ion_closed, plan, p, T, gl6, td, tc, ud,
                                        uc);
                 if (!ion_closed) terms_b[row * nodes + i] = make_double2(ud, uc);
             } else {
-                table_node_terms<(PROCESS == 4 ? 0 : PROCESS)>(i, k, lbh.x, lbh.y, plan, p, T, gl6,
+                table_node_terms<(PROCESS >= 4 ? 0 : PROCESS)>(i, k, lbh.x, lbh.y, plan, p, T, gl6,
                                                                 td, tc);
             }
             row_terms[i] = make_double2(td, tc);
@@ -497,7 +526,7 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
 // kernel filled with short units -- was measured and lost 0.4 % / 1.3 % on a full / a 1/8 share:
 // the combined kernel spills 148 B against 68; profiles/r02_flat_table_study.md.)
 struct FlatQueues {
-    double2 *terms_a, *terms_b;     // terms of the process; of ionisation in the fused pass
+    double2 *terms_a, *terms_b, *terms_c;   // terms of the process; of the processes riding with it
     uint32_t *queue_a;
 };
 
@@ -519,7 +548,8 @@ table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__re
     // (another process: other terms) may fill SMs as they free up.
     if (fp.first_launch) pdl_wait_prerequisites();
     pdl_release_dependents();
-    flat_run_units<PROCESS>(K, nK, rowpar, fq.terms_a, fq.terms_b, fq.queue_a, fp, p, T, s_gl6);
+    flat_run_units<PROCESS>(K, nK, rowpar, fq.terms_a, fq.terms_b, fq.terms_c, fq.queue_a, fp, p, T,
+                            s_gl6);
     // completion order along the chain: this kernel does not retire before its predecessor has,
     // so the summation kernel only has to wait for the last one
     __syncthreads();
