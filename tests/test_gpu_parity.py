@@ -368,6 +368,27 @@ def test_flat_tables_process_subsets(mask):
             assert float(d[pr.index].abs().sum()) == 0.0 and float(c[pr.index].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("mask", [15, 13, 9, 5])
+def test_flat_tables_with_many_rows(port, mask):
+    """From 4 096 rows on bremsstrahlung and ionisation ride on the photonuclear kernel's nodes
+    (one exp for three integrands): same bits as the row-per-CTA form and as the oracle, for every
+    process subset that takes or just misses that path."""
+    n = 4500
+    K = grids.table_energies(n, -2.0, 6.0)
+    Kd = dev(K)
+    procs = tuple(pr for pr in dcs.PROCESSES if (mask >> pr.index) & 1)
+    d_flat, c_flat = dcs.cuda.tables(Kd, 0.05, ELEMENTS["Fe"], MUON_MASS, 31, processes=procs,
+                                     flat=True)
+    d_rows, c_rows = dcs.cuda.tables(Kd, 0.05, ELEMENTS["Fe"], MUON_MASS, 31, processes=procs,
+                                     flat=False)
+    assert torch.equal(d_flat, d_rows) and torch.equal(c_flat, c_rows)
+    idx = np.arange(0, n, 53)
+    for pr in procs:
+        want = port.vmap_integral(pr.index, 1, K[idx], 0.05, 31, ELEMENTS["Fe"], MUON_MASS,
+                                  threads=8)
+        assert_parity(c_flat[pr.index][torch.from_numpy(idx).cuda()], want, (mask, pr.name))
+
+
 def test_table_workspace_contract():
     """C ABI: noa_dcs_table_workspace_doubles sizes the workspace; a NULL or short workspace makes
     noa_dcs_table_ws_f64 fall back to the row-per-CTA launches (same bits); the exchange form
