@@ -29,7 +29,7 @@ def main(path, commit):
     out = {"source": f"ncu --set full of tools/profile_kernels.py ({path})", "commit": commit,
            "note": "instr per eval = warp instructions per warp of 32 evaluations (full warps); "
                    "table_build_* = sums over the chained kernels of one config-4 build (row "
-                   "parameters, three terms kernels, summation); "
+                   "parameters, terms kernels, summation); "
                    "fp64 instructions counted as sm__inst_executed_pipe_fp64.sum x 32 lanes"}
     table = {"fp64": 0.0, "inst": 0.0, "dram": 0.0, "ms": {}}
     for d in data:
@@ -56,7 +56,8 @@ def main(path, commit):
             if "table_terms_kernel<" in name:
                 m = name.split("table_terms_kernel<")[1].split(">")[0].strip().replace("(int)", "")
                 key = {"0": "bremsstrahlung", "1": "pair_production", "2": "photonuclear",
-                       "3": "ionisation", "4": "bremsstrahlung+ionisation"}.get(m, m)
+                       "3": "ionisation", "4": "bremsstrahlung+ionisation",
+                       "6": "photonuclear+bremsstrahlung+ionisation"}.get(m, m)
             else:
                 key = "summation" if "table_sum_kernel" in name else "row_parameters"
             table["fp64"] += fp64 * 32
