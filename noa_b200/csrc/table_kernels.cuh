@@ -396,24 +396,26 @@ __device__ __forceinline__ void table_node_terms_light(uint32_t i, double k, dou
 
 // ---- flat form (builds that come with a workspace for the node terms) ----------------------------
 // With 16 B of workspace per node the rows need no CTA-per-row structure at all:
-//   table_rowpar_kernel      {ln(K xlow), h} of every row
-//   table_terms_kernel<P>    every (row, node) of process P as one flat index space, 256
-//                            consecutive nodes per CTA iteration, chunks dealt round-robin to a
-//                            persistent grid: no barrier, no summation phase, warps never wait for
-//                            each other, and the schedule is balanced to a 256-node chunk whatever
-//                            the number of rows -- one rank of eight has 1 250 rows per process,
-//                            where the row-per-CTA forms leave the two cheap processes
-//                            latency-bound on a partial wave and the heavy ones ragged;
-//   table_sum_kernel         one warp per (process, row): coalesced 512-byte reads of the terms,
-//                            res += term in node order by shuffle broadcast (every lane carries
-//                            both running sums), / (K + mass) -- or the closed form of an
-//                            ionisation row -- stored to the local table and every peer's; in the
-//                            exchange form its last CTA runs the rank barrier.
+//   table_rowpar_kernel      {ln(K xlow), h} of every row; zeroes the queue words
+//   table_terms_kernel<P>    every (row, node) of process P as one flat index space cut into
+//                            units of 32 consecutive nodes of one row (8 x 32 for the two cheap
+//                            processes) that WARPS pop from a device-side queue, rows in
+//                            descending energy: no barrier, no summation phase, warps never wait
+//                            for each other, and the schedule is balanced to a unit whatever the
+//                            number of rows.  (Static deals of 256-node chunks to a persistent
+//                            grid were built first and lost: a chunk of out-of-range nodes is
+//                            free, and 4 chunks per row lock onto a grid of 4 x 111 CTAs.)
+//   table_sum_kernel         one warp per (process, row): the row's terms through a cp.async
+//                            ring in shared memory, res += term in node order by lanes 0 / 1,
+//                            / (K + mass) -- or the closed form of an ionisation row -- stored to
+//                            the local table and every peer's; in the exchange form its last CTA
+//                            runs the rank barrier.
 // The launches of a build are chained with programmatic dependent launch.  The terms make one
 // round trip through L2 / HBM (160 MB each way per process on config 4, hidden under the
 // FP64-bound evaluation); what is bought is the 4.4 us of two-lane summation per row during which
 // the other 254 threads of the row's CTA idled (barrier stalls: 14 % of the pair kernel's warp
-// cycles, 8 % of photonuclear's, profiles/r02_ncu_full_s3.md).
+// cycles, 8 % of photonuclear's, profiles/r02_ncu_full_s3.md).  Every variant tried on the way is
+// in profiles/r02_flat_table_study.md.
 struct FlatPlan {
     uint32_t cells;
     int32_t second_power;
