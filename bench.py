@@ -900,6 +900,28 @@ def run_extras(c):
         ms = c_local_timed(c, lambda i: dcs.soft_scattering(ms1, Kt, el, mass))
         out["soft_scattering_1e4"] = {"ms": ms, "energies": n, "gpus": 1,
                                       "photonuclear_evals_per_s": n * 102 / (ms * 1e-3)}
+        # per-material table assembly (PUMAS's steps over NOA's DCS), water, 180 nodes
+        import oracle
+        water = physics.WATER
+        asm = {}
+        ms = c_local_timed(c, lambda i: asm.update(
+            dcs.cuda.material_assembly(Kt, X_LOW, water, mass, 180)), reps=8, warm=2)
+        t0 = time.perf_counter()
+        want = oracle.material_assembly(checker, [tuple(e) for e in water.elements],
+                                        list(water.fractions), MUON_MASS,
+                                        grids.table_energies(N_K), X_LOW, 180,
+                                        threads=checker.max_threads)
+        cpu_s = time.perf_counter() - t0
+        same = all(np.array_equal(asm[k].cpu().numpy().reshape(want[k].shape), want[k],
+                                  equal_nan=True)
+                   for k in ("elem", "cs", "cel", "straggling", "csf", "cs_total", "xt"))
+        same = same and float(asm["kt"].item()) == want["kt"] and int(asm["it"].item()) == want["it"]
+        out["material_assembly_water_1e4"] = {
+            "ms": ms, "energies": n, "nodes": 180, "elements": 2, "gpus": 1,
+            "parity": {"bit_exact": bool(same), "against": f"oracle/material_oracle.c over the {kind} "
+                       "DCS: every array (element tables, mix, cumulative fractions, threshold "
+                       "row, x_t search) of all 10^4 energies"},
+            "cpu_baseline": {"seconds": cpu_s, "cores": checker.max_threads, "kind": kind}}
     del bufs
     out["multi_material_sweep_2^28"] = run_sweep(c, Kt, checker, kind)
     return out
