@@ -137,7 +137,8 @@ int noa_dcs_table_ws_f64(unsigned process_mask, const double *K, int64_t nK, dou
 int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
                                int32_t min_points, int32_t n_elements, const double *A,
                                const double *I, const int32_t *Z, const double *w, double mass,
-                               double *scratch, double *table, void *stream);
+                               double *scratch, double *table, double *workspace,
+                               int64_t workspace_doubles, void *stream);
 
 /*
  * Multi-GPU form of noa_dcs_table_f64: builds the rows of the energies K_local[0 .. n_local) and
@@ -235,14 +236,16 @@ int noa_dcs_vmap_integral_mode_f64(int process, int mode, const double *K, doubl
  *   xt         [n_elements][4][nK]  fractional threshold per process, element and energy: 1 below
  *              row `it`, else doubling from `cutoff` until the DCS is positive followed by a
  *              bisection to 1 % of the cutoff                     pumas.c:10839-10880
- * 4 n_elements + 3 launches (+ the chained table launches), all on `stream`.
+ * 4 n_elements + 3 launches (+ the chained table launches), all on `stream`.  `workspace`
+ * (optional, NULL allowed): as in noa_dcs_table_ws_f64, sized for nK rows; the element tables are
+ * then built in the flat form.
  */
 int noa_dcs_material_assembly_f64(const double *K, int64_t nK, double cutoff, int32_t min_points,
                                   int32_t n_elements, const double *A, const double *I,
                                   const int32_t *Z, const double *w, double mass, double *elem,
                                   double *cs, double *cel, double *straggling, double *csf,
                                   double *cs_total, double *kt, int32_t *it, double *xt,
-                                  void *stream);
+                                  double *workspace, int64_t workspace_doubles, void *stream);
 
 /*
  * Coulomb scattering and soft scattering -- the rest of the reference's dcs.hh surface

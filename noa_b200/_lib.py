@@ -38,7 +38,7 @@ SIGNATURES = {
     "noa_dcs_table_material_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _i32,
                                                   ctypes.POINTER(_f64), ctypes.POINTER(_f64),
                                                   ctypes.POINTER(_i32), ctypes.POINTER(_f64), _f64,
-                                                  _vp, _vp, _vp]),
+                                                  _vp, _vp, _vp, _i64, _vp]),
     "noa_dcs_table_scatter_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
                                                  _i32, _f64, _i32, ctypes.POINTER(_vp),
                                                  ctypes.POINTER(_vp), _i64, _i64, _i64, _vp]),
@@ -60,7 +60,7 @@ SIGNATURES = {
                                                      ctypes.POINTER(_f64), ctypes.POINTER(_f64),
                                                      ctypes.POINTER(_i32), ctypes.POINTER(_f64),
                                                      _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                                     _vp, _vp]),
+                                                     _vp, _vp, _i64, _vp]),
     "noa_dcs_coulomb_data_f64": (ctypes.c_int, [_vp, _i64, _f64, _f64, _i32, _f64, _vp, _vp, _vp,
                                                 _vp, _vp]),
     "noa_dcs_coulomb_transport_f64": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),

@@ -728,7 +728,8 @@ int noa_dcs_table_ws_f64(unsigned process_mask, const double *K, int64_t nK, dou
 int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t nK, double xlow,
                                int32_t min_points, int32_t n_elements, const double *A,
                                const double *I, const int32_t *Z, const double *w, double mass,
-                               double *scratch, double *table, void *stream) {
+                               double *scratch, double *table, double *workspace,
+                               int64_t workspace_doubles, void *stream) {
     if (n_elements < 1 || n_elements > NOA_DCS_MAX_ELEMENTS || !A || !I || !Z || !w)
         return NOA_DCS_EINVAL;
     if (process_mask == 0 || process_mask > 15u || nK < 0 || min_points < 1) return NOA_DCS_EINVAL;
@@ -741,8 +742,11 @@ int noa_dcs_table_material_f64(unsigned process_mask, const double *K, int64_t n
         m.w[el] = w[el];
         double *part = scratch + (int64_t) el * columns;
         // rows of processes outside the mask are zeroed by the build itself
+        TableOptions opt;
+        opt.workspace = workspace;
+        opt.workspace_doubles = workspace_doubles;
         int rc = table_impl(process_mask, false, K, nK, xlow, min_points, A[el], I[el], Z[el], mass,
-                            local_out(part, part + 4 * nK, nK), stream);
+                            local_out(part, part + 4 * nK, nK), stream, opt);
         if (rc) return rc;
     }
     const int64_t blocks = (columns + 255) / 256;
@@ -845,7 +849,7 @@ int noa_dcs_material_assembly_f64(const double *K, int64_t nK, double cutoff, in
                                   const int32_t *Z, const double *w, double mass, double *elem,
                                   double *cs, double *cel, double *straggling, double *csf,
                                   double *cs_total, double *kt, int32_t *it, double *xt,
-                                  void *stream) {
+                                  double *workspace, int64_t workspace_doubles, void *stream) {
     if (n_elements < 1 || n_elements > NOA_DCS_MAX_ELEMENTS || !A || !I || !Z || !w)
         return NOA_DCS_EINVAL;
     if (nK < 0 || min_points < 1 || !(cutoff > 1E-06) || !(cutoff < 1.)) return NOA_DCS_EINVAL;
@@ -863,8 +867,11 @@ int noa_dcs_material_assembly_f64(const double *K, int64_t nK, double cutoff, in
         mw.w[el] = mp.w[el] = w[el];
         mp.p[el] = make_params(A[el], I[el], Z[el], mass);
         double *e = elem + (int64_t) el * 3 * n4;
+        TableOptions opt;
+        opt.workspace = workspace;
+        opt.workspace_doubles = workspace_doubles;
         int rc = table_impl(15u, false, K, nK, cutoff, min_points, A[el], I[el], Z[el], mass,
-                            local_out(e, e + n4, nK), s);
+                            local_out(e, e + n4, nK), s, opt);
         if (rc) return rc;
         cudaError_t ce = cudaMemsetAsync(e + 2 * n4, 0, (size_t) n4 * sizeof(double), s);
         if (ce != cudaSuccess) return (int) ce;

@@ -439,9 +439,11 @@ class _Cuda:
         w = (ctypes.c_double * ne)(*[float(f) for f in material.fractions])
         if n:
             with torch.cuda.device(dev):
+                need = int(lib.noa_dcs_table_workspace_doubles(n, int(min_points)))
+                ws = _table_workspace(dev, need)
                 _lib.check(lib.noa_dcs_table_material_f64(
                     mask, _ptr(kinetic_energies), n, float(xlow), int(min_points), ne, A, I, Z, w,
-                    float(mass), _ptr(scratch), _ptr(table), _stream(dev)))
+                    float(mass), _ptr(scratch), _ptr(table), _ptr(ws), need, _stream(dev)))
         return table, scratch.view(ne, 2, 4, n)
 
 
@@ -483,11 +485,14 @@ class _Cuda:
         w = (ctypes.c_double * ne)(*[float(f) for f in material.fractions])
         if n:
             with torch.cuda.device(dev):
+                need = int(lib.noa_dcs_table_workspace_doubles(n, int(min_points)))
+                ws = _table_workspace(dev, need)
                 _lib.check(lib.noa_dcs_material_assembly_f64(
                     _ptr(kinetic_energies), n, float(cutoff), int(min_points), ne, A, I, Z, w,
                     float(mass), _ptr(out["elem"]), _ptr(out["cs"]), _ptr(out["cel"]),
                     _ptr(out["straggling"]), _ptr(out["csf"]), _ptr(out["cs_total"]),
-                    _ptr(out["kt"]), _ptr(out["it"]), _ptr(out["xt"]), _stream(dev)))
+                    _ptr(out["kt"]), _ptr(out["it"]), _ptr(out["xt"]), _ptr(ws), need,
+                    _stream(dev)))
         return out
 
 
