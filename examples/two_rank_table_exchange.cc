@@ -96,6 +96,8 @@ static int run_rank(int rank, int sock) {
         }
         CHECK(noa_dcs_table_exchange_f64(0xF, d_K_local, (int64_t) K_local.size(), xlow,
                                          min_points, A, I, Z, mass, world, rank, del, cel, flags,
+                                         /*multicast_del=*/nullptr, /*multicast_cel=*/nullptr,
+                                         /*multicast_flags=*/nullptr,
                                          d_sync, d_scratch, scratch_doubles, epoch, n,
                                          /*first_row=*/rank,
                                          /*row_stride=*/world, /*timeout_seconds=*/20., stream));

@@ -171,7 +171,14 @@ int noa_dcs_table_scatter_f64(unsigned process_mask, const double *K_local, int6
  * (scratch_doubles >= noa_dcs_table_workspace_doubles(n_local, min_points), else
  * NOA_DCS_EINVAL): the exchange build is the flat form -- terms kernels over the local (row, node)
  * space, then the summation kernel, which stores every finished row into all n_peers tables and
- * whose last CTA runs the flag exchange.  A peer that does not arrive within `timeout_seconds` of wall-clock time
+ * whose last CTA runs the flag exchange.
+ * `multicast_del` / `multicast_cel` (optional, both or neither; NULL otherwise) = NVSwitch
+ * multicast addresses that alias the DEL / CEL halves of ALL n_peers destination tables (a CUDA
+ * multicast object bound to the same allocations, e.g. torch symmetric memory's `multicast_ptr`):
+ * each finished value is then written with ONE `multimem.st` that the switch replicates into every
+ * GPU's table, this one's included, instead of n_peers stores.  `multicast_flags` (optional, only
+ * with the two above) = the same kind of alias of the flag arrays: the epoch is then published to
+ * all peers with one store as well.  A peer that does not arrive within `timeout_seconds` of wall-clock time
  * (<= 0: NOA_DCS_DEFAULT_EXCHANGE_TIMEOUT_S) is FATAL: the timeout count is bumped and the kernel
  * traps, so the stream reports a launch failure instead of handing back a partial table.
  */
@@ -179,7 +186,9 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
                                double xlow, int32_t min_points, double A, double I, int32_t Z,
                                double mass, int32_t n_peers, int32_t my_peer,
                                double *const *peer_del, double *const *peer_cel,
-                               uint32_t *const *peer_flags, uint32_t *sync, double *scratch,
+                               uint32_t *const *peer_flags, double *multicast_del,
+                               double *multicast_cel, uint32_t *multicast_flags, uint32_t *sync,
+                               double *scratch,
                                int64_t scratch_doubles, uint32_t epoch, int64_t n_total,
                                int64_t first_row, int64_t row_stride, double timeout_seconds,
                                void *stream);

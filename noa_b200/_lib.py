@@ -45,8 +45,8 @@ SIGNATURES = {
     "noa_dcs_table_exchange_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64,
                                                   _i32, _f64, _i32, _i32, ctypes.POINTER(_vp),
                                                   ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp,
-                                                  _vp, _i64, ctypes.c_uint32, _i64, _i64, _i64,
-                                                  _f64, _vp]),
+                                                  _vp, _vp, _vp, _vp, _i64, ctypes.c_uint32, _i64,
+                                                  _i64, _i64, _f64, _vp]),
     "noa_dcs_table_workspace_doubles": (_i64, [_i64, _i32]),
     "noa_dcs_table_ws_f64": (ctypes.c_int, [ctypes.c_uint, _vp, _i64, _f64, _i32, _f64, _f64, _i32,
                                             _f64, _vp, _vp, _vp, _i64, _vp]),

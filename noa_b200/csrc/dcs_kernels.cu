@@ -782,7 +782,9 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
                                double xlow, int32_t min_points, double A, double I, int32_t Z,
                                double mass, int32_t n_peers, int32_t my_peer,
                                double *const *peer_del, double *const *peer_cel,
-                               uint32_t *const *peer_flags, uint32_t *sync, double *scratch,
+                               uint32_t *const *peer_flags, double *multicast_del,
+                               double *multicast_cel, uint32_t *multicast_flags, uint32_t *sync,
+                               double *scratch,
                                int64_t scratch_doubles, uint32_t epoch, int64_t n_total,
                                int64_t first_row, int64_t row_stride, double timeout_seconds,
                                void *stream) {
@@ -799,6 +801,11 @@ int noa_dcs_table_exchange_f64(unsigned process_mask, const double *K_local, int
     out.first_row = first_row;
     out.row_stride = row_stride;
     out.sync = sync;
+    if (multicast_del && multicast_cel) {
+        out.mc_del = multicast_del;
+        out.mc_cel = multicast_cel;
+        out.mc_flags = multicast_flags;
+    }
     out.epoch = epoch;
     out.timeout_ns = (uint64_t) (timeout_seconds * 1e9);
     for (int j = 0; j < n_peers; j++) {

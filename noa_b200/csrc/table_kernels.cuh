@@ -72,6 +72,10 @@ struct TableOut {
     // sync = this GPU's words {CTA counter, timeouts, 6 reserved}; flags[0] == nullptr otherwise
     uint32_t *flags[NOA_DCS_MAX_PEERS];
     uint32_t *sync;
+    // NVSwitch multicast addresses of the destination table (exchange form, optional): one
+    // multimem.st reaches every GPU's copy, this one's included, instead of n_peers stores
+    double *mc_del, *mc_cel;
+    uint32_t *mc_flags;       // multicast alias of the flag arrays (all peers' at once), or nullptr
     uint32_t epoch;
     uint32_t total_ctas;      // CTAs of all launches of this build (the last one to finish signals)
     uint64_t timeout_ns;      // how long to wait for a peer before giving up (trap)
@@ -134,10 +138,17 @@ __device__ __forceinline__ void table_exchange_tail(const TableOut &out) {
     // re-armed for the next build on this stream
     out.sync[0] = 0;
     __threadfence_system();
-    for (int j = 0; j < out.n_peers; j++)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(out.flags[j] + out.me),
+    if (out.mc_flags != nullptr) {
+        // one store, replicated by the switch into slot `me` of every peer's flag array
+        asm volatile("multimem.st.release.sys.global.b32 [%0], %1;" ::"l"(out.mc_flags + out.me),
                      "r"(out.epoch)
                      : "memory");
+    } else {
+        for (int j = 0; j < out.n_peers; j++)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(out.flags[j] + out.me),
+                         "r"(out.epoch)
+                         : "memory");
+    }
     const uint64_t t0 = global_timer_ns();
     for (int j = 0; j < (NOA_XCHG_NO_WAIT ? 0 : out.n_peers); j++) {
         const uint32_t *slot = out.flags[out.me] + j;
@@ -647,8 +658,15 @@ table_sum_kernel(const double *__restrict__ K, int64_t nK, uint32_t nodes,
                                         : acc / (k + p.mass);
                 const int64_t at = (int64_t) fs.out_row[slot] * out.n_total + out.first_row +
                                    row * out.row_stride;
-                for (int j = 0; j < out.n_peers; j++)
-                    if (!NOA_XCHG_NO_REMOTE || j == out.me) dst[j][at] = v;
+                double *mc = lane ? out.mc_cel : out.mc_del;
+                if (mc != nullptr && !NOA_XCHG_NO_REMOTE) {
+                    // the switch replicates the store into all n_peers tables
+                    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + at), "d"(v)
+                                 : "memory");
+                } else {
+                    for (int j = 0; j < out.n_peers; j++)
+                        if (!NOA_XCHG_NO_REMOTE || j == out.me) dst[j][at] = v;
+                }
                 // scatter form without flags: the writer lanes fence their own remote stores
                 if (out.n_peers > 1 && out.flags[0] == nullptr) __threadfence_system();
             }

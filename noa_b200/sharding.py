@@ -10,6 +10,8 @@ Every (K, q) evaluation and every table row is independent, so:
     rank holds the complete [2 (DEL, CEL), 4 (process), n_K] table (`TableBuilder`).
 The per-rank message is n_K/W x 8 columns x 8 B (80 kB at n_K = 10^4, W = 8): latency-bound.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -180,7 +182,7 @@ class PeerTableBuilder(_HostTables):
     FLAG_WORDS = 16     # NOA_DCS_MAX_PEERS 32-bit epoch slots
 
     def __init__(self, K, rank, world, group=None, fused_barrier=True, timeout_s=30.0,
-                 arm=True):
+                 arm=True, multicast=True):
         import ctypes
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
@@ -210,6 +212,18 @@ class PeerTableBuilder(_HostTables):
         self._del = [(vp * world)(*[p + b * per_table * 8 for p in ptrs]) for b in range(2)]
         self._cel = [(vp * world)(*[p + b * per_table * 8 + half for p in ptrs]) for b in range(2)]
         self._flags = (vp * world)(*[p + 2 * per_table * 8 for p in ptrs])
+        # NVSwitch multicast alias of the same allocation (0 = not available on this box / group):
+        # one multimem.st per value then reaches every rank's table
+        mc = 0
+        if multicast and os.environ.get("NOA_DCS_NO_MULTICAST", "0") != "1":
+            try:
+                mc = int(self.handle.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+        self.multicast = mc != 0
+        self._mc_del = [vp(mc + b * per_table * 8) if mc else None for b in range(2)]
+        self._mc_cel = [vp(mc + b * per_table * 8 + half) if mc else None for b in range(2)]
+        self._mc_flags = vp(mc + 2 * per_table * 8) if mc else None
         # {CTA counter, timeouts, 6 reserved} (noa_dcs_table_exchange_f64: `sync`)
         self.done = torch.zeros(8, dtype=torch.int32, device=K.device)
         # workspace of the flat form (node terms), sized at the first build
@@ -246,7 +260,8 @@ class PeerTableBuilder(_HostTables):
                 self._lib.check(self.lib.noa_dcs_table_exchange_f64(
                     mask, c.c_void_p(self.K_local.data_ptr()), self.n_local, float(xlow),
                     int(min_points), float(A), float(I), int(Z), float(mass), self.world, self.rank,
-                    self._del[b], self._cel[b], self._flags, c.c_void_p(self.done.data_ptr()),
+                    self._del[b], self._cel[b], self._flags, self._mc_del[b], self._mc_cel[b],
+                    self._mc_flags, c.c_void_p(self.done.data_ptr()),
                     c.c_void_p(self.scratch.data_ptr()), self.scratch.numel(),
                     self.epoch, self.n, self.rank, self.world, self.timeout_s, stream))
             else:

@@ -419,14 +419,14 @@ def test_table_workspace_contract():
     t = tabs[0]
     dl, cl, fl = (vp * 1)(t.data_ptr()), (vp * 1)(t.data_ptr() + 4 * n * 8), (vp * 1)(flags.data_ptr())
     rc = lib.noa_dcs_table_exchange_f64(15, vp(K.data_ptr()), n, 0.05, mp, 22., 0.1364e-6, 11,
-                                        MUON_MASS, 1, 0, dl, cl, fl, vp(sync.data_ptr()), None, 0,
+                                        MUON_MASS, 1, 0, dl, cl, fl, None, None, None, vp(sync.data_ptr()), None, 0,
                                         1, n, 0, 1, 5.0, stream)
     assert rc == -1      # NOA_DCS_EINVAL
     # ... and with one: the same table
     t2 = torch.zeros((2, 4, n), dtype=torch.float64, device="cuda")
     dl2, cl2 = (vp * 1)(t2.data_ptr()), (vp * 1)(t2.data_ptr() + 4 * n * 8)
     _lib.check(lib.noa_dcs_table_exchange_f64(15, vp(K.data_ptr()), n, 0.05, mp, 22., 0.1364e-6,
-                                              11, MUON_MASS, 1, 0, dl2, cl2, fl,
+                                              11, MUON_MASS, 1, 0, dl2, cl2, fl, None, None, None,
                                               vp(sync.data_ptr()), vp(ws.data_ptr()), need, 1, n,
                                               0, 1, 5.0, stream))
     torch.cuda.synchronize()

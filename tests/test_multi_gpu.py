@@ -56,9 +56,17 @@ def _worker(rank, world, port, n_rows, tmp):
         seq.append(peer.build(0.05, el, MUON_MASS, 60 + 6 * (i % 2)).clone())
     torch.cuda.synchronize()
     timeouts = peer.timeouts() if hasattr(peer, "timeouts") else 0
+    # the peer form with per-peer stores instead of NVSwitch multicast stores (what a box without
+    # multicast support, or a C++ host that only has CUDA-IPC mappings, runs)
+    multicast = bool(getattr(peer, "multicast", False))
+    unicast = sharding.PeerTableBuilder(K, rank, world, multicast=False) \
+        if kind == "PeerTableBuilder" else peer
+    e = unicast.build(0.05, ELEMENTS["rock"], MUON_MASS, 180)
+    torch.cuda.synchronize()
+    e = e.clone()
     np.savez(os.path.join(tmp, f"r{rank}.npz"), gather=a.cpu().numpy(), peer=b.cpu().numpy(),
              again=c.cpu().numpy(), two_step=d.cpu().numpy(), kind=kind, timeouts=timeouts,
-             seq=torch.stack(seq).cpu().numpy())
+             seq=torch.stack(seq).cpu().numpy(), unicast=e.cpu().numpy(), multicast=multicast)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,12 +88,13 @@ def test_multi_rank_table_build(tmp_path, world, n_rows):
         # rows of the processes a masked build did not ask for are zero on every rank
         assert not got["again"][:, [0, 2, 3]].any(), f"stale rows after a masked build, rank {r}"
         assert np.array_equal(got["two_step"], want), f"two-step peer build differs on rank {r}"
+        assert np.array_equal(got["unicast"], want), f"unicast peer build differs on rank {r}"
         assert int(got["timeouts"]) == 0
         for i in range(12):
             el = ELEMENTS["Pb"] if i % 3 == 1 else ELEMENTS["rock"]
             di, ci = dcs.cuda.tables(K, 0.05, el, MUON_MASS, 60 + 6 * (i % 2))
             assert np.array_equal(got["seq"][i], torch.stack((di, ci)).cpu().numpy()), (r, i)
-        print("rank", r, "builder:", got["kind"])
+        print("rank", r, "builder:", got["kind"], "multicast stores:", bool(got["multicast"]))
 
 
 def test_cpp_two_rank_ipc_example():

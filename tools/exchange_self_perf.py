@@ -24,7 +24,7 @@ for W in (1, 2, 4, 8):
     def build():
         epoch[0] += 1
         _lib.check(lib.noa_dcs_table_exchange_f64(15, vp(Kl.data_ptr()), n, 0.05, 1000, 22., 0.1364e-6, 11, MUON_MASS,
-                   1, 0, dl, cl, fl, vp(sync.data_ptr()), vp(scratch.data_ptr()), scratch.numel(), epoch[0], n, 0, 1, 10.0,
+                   1, 0, dl, cl, fl, None, None, None, vp(sync.data_ptr()), vp(scratch.data_ptr()), scratch.numel(), epoch[0], n, 0, 1, 10.0,
                    vp(torch.cuda.current_stream().cuda_stream)))
     for _ in range(3): build()
     torch.cuda.synchronize(); ts = []

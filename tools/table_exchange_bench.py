@@ -34,5 +34,8 @@ if world > 1:
     out["peer_two_step_ms"] = timed(lambda: two.build(0.05, STANDARD_ROCK, MUON_MASS, mp))
     fused = sharding.PeerTableBuilder(K, rank, world)
     out["peer_fused_ms"] = timed(lambda: fused.build(0.05, STANDARD_ROCK, MUON_MASS, mp))
+    out["multicast_stores"] = fused.multicast
+    uni = sharding.PeerTableBuilder(K, rank, world, multicast=False)
+    out["peer_fused_unicast_ms"] = timed(lambda: uni.build(0.05, STANDARD_ROCK, MUON_MASS, mp))
 if rank == 0: print(json.dumps(out), flush=True)
 dist.barrier(); dist.destroy_process_group()
