@@ -8,9 +8,13 @@
 //                           loads of K and of q issued before the first evaluation)
 //   vmap_all_kernel         the four processes of one pair in one pass (16 B in, 32 B out)
 //   vmap_mixture_element_kernel   one element's term of sum_e w_e * DCS_e (water = H + O)
-//   table_kernel<MASK, PERSISTENT>  (table_kernels.cuh) rows of the DEL/CEL tables: nodes of the
-//                           composite 6-point rule across threads, node terms staged in shared
-//                           memory and accumulated in the reference's serial order
+//   table_rowpar / table_terms<P> / table_sum   (table_kernels.cuh) the DEL/CEL tables in the flat
+//                           form: (row, node) units popped by warps, node terms through a
+//                           workspace, summation in the reference's serial order by a second
+//                           kernel that also delivers the rows (peers included, NVSwitch multicast
+//                           stores, rank barrier) -- noa_dcs_table_ws_f64, noa_dcs_table_exchange_f64
+//   table_kernel<MASK>      the same tables with one CTA per row and the terms in shared memory,
+//                           for the calls that bring no workspace
 //   threshold / straggling  (material_kernels.cuh) the per-material table assembly of SURVEY 8(f1)
 //   coulomb_* / soft_scattering   (coulomb_kernels.cuh)
 // Measurement kernels (FP64 pipe probes, the node-per-lane pair-production variant) live in

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Single-GPU timing of the PERSISTENT (exchange) form of the table build on a 1/W share of config
-4's rows: noa_dcs_table_exchange_f64 with this GPU as its only peer.  Shows what one rank of W pays
-for its compute, without needing W GPUs.  Usage: [NOA_DCS_TABLE_LAUNCH=split|combined] python
-tools/exchange_self_perf.py"""
+"""Single-GPU timing of the EXCHANGE form of the table build on a 1/W share of config 4's rows:
+noa_dcs_table_exchange_f64 with this GPU as its only peer, against dcs.cuda.tables on the same rows.
+Shows what one rank of W pays for its compute and for the exchange machinery (fences, flags)
+without needing W GPUs.  Usage: python tools/exchange_self_perf.py"""
 import ctypes, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
