@@ -116,7 +116,7 @@ int noa_dcs_table_f64(unsigned process_mask, const double *K, int64_t nK, double
  * a node make one round trip through `workspace`, and one summation kernel adds each row's terms
  * up in node order (numerics.hh:84-87) -- the same additions in the same order, so the same bits
  * as noa_dcs_table_f64.  `workspace` = device array of at least
- * noa_dcs_table_workspace_doubles(nK, min_points) doubles (2 nK + 8 nK * 6 ceil(min_points / 6):
+ * noa_dcs_table_workspace_doubles(nK, min_points) doubles (4 nK + 2 + 8 nK * 6 ceil(min_points / 6):
  * 16 B per node and process), contents irrelevant, free again when the launches have run on
  * `stream`.  A NULL or too small workspace falls back to noa_dcs_table_f64's launches.
  */

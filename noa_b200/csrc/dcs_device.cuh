@@ -134,4 +134,19 @@ __device__ __forceinline__ double dcs_value(double K, double q, const Params &p,
 #endif
 }
 
+// pair production with the kinetic-energy-only part (PairRow) handed in; an evaluation whose
+// flag drops is redone with the plain operations from scratch, as everywhere else
+__device__ __forceinline__ double dcs_value_pair_row(double K, double q, const PairRow &row,
+                                                     const Params &p, const glibm::Tab &T) {
+#if NOA_FOLDED_OPS
+    FoldedOps<true> dv;
+    dv.dens = T.aux_smem;
+    double v = pair_production(K, q, p, T, dv, &row);
+    if (!dv.ok()) v = dcs_eval_plain<1>(K, q, p, T);
+    return v;
+#else
+    return dcs_eval<1>(K, q, p, T);
+#endif
+}
+
 }  // namespace noa_b200

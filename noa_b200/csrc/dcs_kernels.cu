@@ -360,10 +360,10 @@ struct TableOptions {
 
 static int64_t table_nodes(int32_t min_points) { return ((int64_t) min_points + 5) / 6 * 6; }
 
-// {ln(K xlow), h} per row + 4 queue words + 4 processes x nK rows x nodes x {DEL term, CEL term}
+// {ln(K xlow), h} and {gamma, zeta} per row + 4 queue words + 4 processes x nK rows x nodes x {DEL term, CEL term}
 static int64_t table_workspace_doubles(int64_t nK, int32_t min_points) {
     if (nK <= 0 || min_points < 1) return 0;
-    return 2 * nK + 2 + 8 * nK * table_nodes(min_points);
+    return 4 * nK + 2 + 8 * nK * table_nodes(min_points);
 }
 
 template <typename... KArgs, typename... Args>
@@ -421,8 +421,10 @@ static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, d
     const int64_t nodes = table_nodes(min_points);
     double2 *rowpar = reinterpret_cast<double2 *>(opt.workspace);
     uint32_t *queues = reinterpret_cast<uint32_t *>(rowpar + nK);
-    double2 *terms = rowpar + nK + 1;
-    table_rowpar_kernel<<<(unsigned) ((nK + 255) / 256), 256, 0, s>>>(K, nK, fp, rowpar, queues);
+    double2 *pairrow = rowpar + nK + 1;
+    double2 *terms = pairrow + nK;
+    table_rowpar_kernel<<<(unsigned) ((nK + 255) / 256), 256, 0, s>>>(K, nK, fp, rowpar, queues,
+                                                                      pairrow, p);
     int rc = after_launch();
     if (rc) return rc;
     static const int heavy_first[4] = {NOA_DCS_PHOTONUCLEAR, NOA_DCS_PAIR_PRODUCTION,
@@ -455,6 +457,7 @@ static int table_flat_impl(unsigned process_mask, const double *K, int64_t nK, d
         const int pr = fs.process[slot];
         FlatQueues fq{};
         fq.terms_a = terms + (int64_t) slot * nK * nodes;
+        fq.pairrow = pairrow;
         fq.queue_a = queues + slot;
         const bool dep = launched;
         if (pr == NOA_DCS_IONISATION && both_light) continue;          // rides with bremsstrahlung

@@ -143,15 +143,45 @@ struct PairKinematics {   // per-(K,q) quantities of src/noa/pms/dcs.hh:159-176
 };
 
 // Kinematic window and integration bound; false = the DCS is exactly 0 (dcs.hh:151-156,174-175)
+// The part of a pair-production value that depends on the kinetic energy alone: the Lorentz factor
+// (dcs.hh:171) and the atomic-electron correction zeta (dcs.hh:229-241).  The table build evaluates
+// ~10^3 recoil energies per kinetic energy, so it computes these once per row
+// (table_rowpar_kernel) and hands them in; same operations on the same operands, same bits.
+struct PairRow {
+    double gamma, zeta;
+};
+
+template <class DV>
+NOA_HD double pair_gamma(double K, const Params &p, DV &dv) {
+    return 1. + dv.div_slot(K, p.mass, kDenMass);
+}
+
+template <class DV>
+NOA_HD double pair_zeta(double gamma, const Params &p, const glibm::Tab &T, DV &dv) {
+    double zeta;
+    if (gamma <= 35.)
+        zeta = 0.;
+    else {
+        zeta = 0.073 * dv.log(dv.div(gamma, 1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
+               0.26;
+        if (zeta <= 0.)
+            zeta = 0.;
+        else
+            zeta = dv.div(zeta, 0.058 * dv.log(dv.div(gamma, 1. + p.p_g2 * gamma * p.p_z13),
+                                                   T) - 0.14);
+    }
+    return zeta;
+}
+
 template <class DV>
 NOA_HD bool pair_setup(double K, double q, const Params &p, const glibm::Tab &T,
-                       PairKinematics &k, DV &dv) {
+                       PairKinematics &k, DV &dv, const PairRow *row = nullptr) {
     if (q <= 4. * kElectronMass) return false;
     if (q >= K + p.p_thr) return false;
     const double nu = dv.div(q, K + p.mass);
     k.beta = dv.div(0.5 * nu * nu, 1. - nu);
     k.xi_factor = p.p_hr2 * k.beta;
-    k.gamma = 1. + dv.div_slot(K, p.mass, kDenMass);
+    k.gamma = row ? row->gamma : pair_gamma(K, p, dv);
     const double x0 = dv.div(4. * kElectronMass, q);
     const double x1 = dv.div(6., k.gamma * (k.gamma - dv.div_slot(q, p.mass, kDenMass)));
     const double argmin = dv.div(x0 + 2. * (1. - x0) * x1, 1. + (1. - x1) * sqrt(1. - x0));
@@ -209,20 +239,9 @@ NOA_HD double pair_node(double t, double q, const PairKinematics &k, const Param
 // Atomic-electron form factor and normalisation (dcs.hh:229-257); `integral` is the 8-node sum
 template <class DV>
 NOA_HD double pair_finish(double K, double q, double integral, const PairKinematics &k,
-                          const Params &p, const glibm::Tab &T, DV &dv) {
-    const double gamma = k.gamma;
-    double zeta;
-    if (gamma <= 35.)
-        zeta = 0.;
-    else {
-        zeta = 0.073 * dv.log(dv.div(gamma, 1. + p.p_g1 * gamma * p.p_z13 * p.p_z13), T) -
-               0.26;
-        if (zeta <= 0.)
-            zeta = 0.;
-        else
-            zeta = dv.div(zeta, 0.058 * dv.log(dv.div(gamma, 1. + p.p_g2 * gamma * p.p_z13),
-                                                   T) - 0.14);
-    }
+                          const Params &p, const glibm::Tab &T, DV &dv,
+                          const PairRow *row = nullptr) {
+    const double zeta = row ? row->zeta : pair_zeta(k.gamma, p, T, dv);
     const double E = K + p.mass;
     const double s = dv.div(p.p_cz * (p.Zd + zeta) * (E - q) * integral, q * E);
     return (s < 0.) ? 0. : dv.div_slot(s * 1E+03 * kAvogadro * (p.mass + K), p.A, kDenA);
@@ -230,14 +249,15 @@ NOA_HD double pair_finish(double K, double q, double integral, const PairKinemat
 
 // One thread does all 8 nodes; accumulation order of numerics.hh:84-87 (h = 1, lb = 0)
 template <class DV>
-NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T, DV &dv) {
+NOA_HD double pair_production(double K, double q, const Params &p, const glibm::Tab &T, DV &dv,
+                              const PairRow *row = nullptr) {
     PairKinematics k;
-    if (!pair_setup(K, q, p, T, k, dv)) return 0.;
+    if (!pair_setup(K, q, p, T, k, dv, row)) return 0.;
     double acc = 0.;
     NOA_NODE_LOOP
     for (int j = 0; j < 8; j++)
         acc += pair_node(NOA_GL(8, x, j), q, k, p, T, dv) * NOA_GL(8, w, j);
-    return pair_finish(K, q, acc, k, p, T, dv);
+    return pair_finish(K, q, acc, k, p, T, dv, row);
 }
 
 // ------------------------------------------------------------------------------------------

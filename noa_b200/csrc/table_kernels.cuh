@@ -439,7 +439,9 @@ struct FlatPlan {
 // zeroes them
 __global__ void table_rowpar_kernel(const double *__restrict__ K, int64_t nK,
                                     const __grid_constant__ FlatPlan plan,
-                                    double2 *__restrict__ rowpar, uint32_t *__restrict__ queues) {
+                                    double2 *__restrict__ rowpar, uint32_t *__restrict__ queues,
+                                    double2 *__restrict__ pairrow,
+                                    const __grid_constant__ Params p) {
     __shared__ glibm::Tables s_tables;
     pdl_release_dependents();       // the first terms kernel may get resident and stage its tables
     const glibm::Tab T = stage_tables(s_tables);
@@ -450,6 +452,10 @@ __global__ void table_rowpar_kernel(const double *__restrict__ K, int64_t nK,
     const double lb = glibm::log(k * plan.xlow, T);
     const double ub = (plan.xhigh == 1.) ? glibm::log(k, T) : glibm::log(k * plan.xhigh, T);
     rowpar[row] = make_double2(lb, (ub - lb) / plan.cells);
+    // what pair production needs of the kinetic energy alone (dcs_math.cuh: PairRow)
+    PlainOps dv;
+    const double gamma = pair_gamma(k, p, dv);
+    pairrow[row] = make_double2(gamma, pair_zeta(gamma, p, T, dv));
 }
 
 // Work unit = kFlatUnit x 32 consecutive nodes of one row, popped by a WARP from a device-side
@@ -479,6 +485,7 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
                                                double2 *__restrict__ terms,
                                                double2 *__restrict__ terms_b,
                                                double2 *__restrict__ terms_c,
+                                               const double2 *__restrict__ pairrow,
                                                uint32_t *__restrict__ queue, const FlatPlan &fp,
                                                const Params &p, const glibm::Tab &T,
                                                const double2 *gl6) {
@@ -520,6 +527,20 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
                     terms_c[row * nodes + i] = make_double2(ud, uc);
                 }
                 table_terms_at<2>(k, q, lbh.y, xw.y, plan, p, T, td, tc);
+            } else if (PROCESS == 1) {
+                // gamma and zeta of the row come from table_rowpar_kernel
+                const double2 gz = __ldcg(pairrow + row);
+                PairRow pre;
+                pre.gamma = gz.x;
+                pre.zeta = gz.y;
+                const uint32_t cell = i / 6u;
+                const double2 xw = gl6[i - cell * 6u];
+                const double q = glibm::exp(lbh.x + lbh.y * (cell + xw.x), T);
+                const double fq = dcs_value_pair_row(k, q, pre, p, T) * q;
+                td = fq * lbh.y * xw.y;
+                double y = fq * q;
+                if (plan.second_power == 3) y *= q;
+                tc = y * lbh.y * xw.y;
             } else if (PROCESS == 4) {
                 double ud = 0., uc = 0.;
                 table_node_terms_light(i, k, lbh.x, lbh.y, !ion_closed, plan, p, T, gl6, td, tc, ud,
@@ -540,6 +561,7 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
 // the combined kernel spills 148 B against 68; profiles/r02_flat_table_study.md.)
 struct FlatQueues {
     double2 *terms_a, *terms_b, *terms_c;   // terms of the process; of the processes riding with it
+    const double2 *pairrow;                 // {gamma, zeta} per row (pair production)
     uint32_t *queue_a;
 };
 
@@ -561,8 +583,8 @@ table_terms_kernel(const double *__restrict__ K, int64_t nK, const double2 *__re
     // (another process: other terms) may fill SMs as they free up.
     if (fp.first_launch) pdl_wait_prerequisites();
     pdl_release_dependents();
-    flat_run_units<PROCESS>(K, nK, rowpar, fq.terms_a, fq.terms_b, fq.terms_c, fq.queue_a, fp, p, T,
-                            s_gl6);
+    flat_run_units<PROCESS>(K, nK, rowpar, fq.terms_a, fq.terms_b, fq.terms_c, fq.pairrow,
+                            fq.queue_a, fp, p, T, s_gl6);
     // completion order along the chain: this kernel does not retire before its predecessor has,
     // so the summation kernel only has to wait for the last one
     __syncthreads();
