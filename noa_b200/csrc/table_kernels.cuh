@@ -101,6 +101,7 @@ struct TableShared {
     double2 gl6[6];                         // {node, weight} of the 6-point rule
     double terms[2 * kTableTerms];          // [node][chain], chain = 2 row + integrand
     double row_k[kTableMaxRows], row_lb[kTableMaxRows], row_h[kTableMaxRows];
+    double row_gamma, row_zeta;             // pair production (one row per item): PairRow
     int64_t row_at[kTableMaxRows];          // destination index of the row, -1 = no such row
     int32_t row_quad[kTableMaxRows];        // 1 = quadrature, 0 = closed form / no row
     int32_t lo, hi;                         // index range of the non-zero terms of the pass
@@ -201,6 +202,21 @@ __device__ __forceinline__ void table_node_terms(uint32_t i, double k, double lb
     tc = y * h * w;
 }
 
+// pair production with the row's {gamma, zeta} handed in
+__device__ __forceinline__ void table_node_terms_pair(uint32_t i, double k, double lb, double h,
+                                                      const PairRow &pre, const TablePlan &plan,
+                                                      const Params &p, const glibm::Tab &T,
+                                                      const double2 *gl6, double &td, double &tc) {
+    const uint32_t cell = i / 6u;
+    const double2 xw = gl6[i - cell * 6u];
+    const double q = glibm::exp(lb + h * (cell + xw.x), T);
+    const double fq = dcs_value_pair_row(k, q, pre, p, T) * q;
+    td = fq * h * xw.y;
+    double y = fq * q;
+    if (plan.second_power == 3) y *= q;
+    tc = y * h * xw.y;
+}
+
 // One item: rows nK-1 - (item R + r), r = 0 .. R-1, of `PROCESS` (descending energy).  Called by
 // every thread of the CTA with the shared buffers free to overwrite.
 template <int PROCESS>
@@ -228,6 +244,12 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
                                                      : glibm::log(k * plan.xhigh, T);
                 s.row_lb[tid] = lb;
                 s.row_h[tid] = (ub - lb) / plan.cells;
+                if (PROCESS == 1) {     // R = 1: what the row's nodes share (dcs_math.cuh: PairRow)
+                    PlainOps dv;
+                    const double gamma = pair_gamma(k, p, dv);
+                    s.row_gamma = gamma;
+                    s.row_zeta = pair_zeta(gamma, p, T, dv);
+                }
             }
         }
         s.row_at[tid] = at;
@@ -266,8 +288,16 @@ __device__ __noinline__ void table_item(uint32_t item, int slot, const double *_
                 }
                 if (!s.row_quad[r]) continue;
                 double td, tc;
-                table_node_terms<PROCESS>(base + il, s.row_k[r], s.row_lb[r], s.row_h[r], plan, p,
-                                          T, s.gl6, td, tc);
+                if (PROCESS == 1) {
+                    PairRow pre;
+                    pre.gamma = s.row_gamma;
+                    pre.zeta = s.row_zeta;
+                    table_node_terms_pair(base + il, s.row_k[0], s.row_lb[0], s.row_h[0], pre, plan,
+                                          p, T, s.gl6, td, tc);
+                } else {
+                    table_node_terms<PROCESS>(base + il, s.row_k[r], s.row_lb[r], s.row_h[r], plan,
+                                              p, T, s.gl6, td, tc);
+                }
                 s.terms[il * CH + 2 * r] = td;
                 s.terms[il * CH + 2 * r + 1] = tc;
                 if (td != 0. || tc != 0.) {             // NaN counts as non-zero
@@ -533,14 +563,7 @@ __device__ __forceinline__ void flat_run_units(const double *__restrict__ K, int
                 PairRow pre;
                 pre.gamma = gz.x;
                 pre.zeta = gz.y;
-                const uint32_t cell = i / 6u;
-                const double2 xw = gl6[i - cell * 6u];
-                const double q = glibm::exp(lbh.x + lbh.y * (cell + xw.x), T);
-                const double fq = dcs_value_pair_row(k, q, pre, p, T) * q;
-                td = fq * lbh.y * xw.y;
-                double y = fq * q;
-                if (plan.second_power == 3) y *= q;
-                tc = y * lbh.y * xw.y;
+                table_node_terms_pair(i, k, lbh.x, lbh.y, pre, plan, p, T, gl6, td, tc);
             } else if (PROCESS == 4) {
                 double ud = 0., uc = 0.;
                 table_node_terms_light(i, k, lbh.x, lbh.y, !ion_closed, plan, p, T, gl6, td, tc, ud,
@@ -601,10 +624,10 @@ struct FlatSum {
 };
 
 #ifndef NOA_SUM_WARPS
-#define NOA_SUM_WARPS 4
+#define NOA_SUM_WARPS 8
 #endif
 #ifndef NOA_SUM_STAGE
-#define NOA_SUM_STAGE 256
+#define NOA_SUM_STAGE 128
 #endif
 // One WARP per (process, row).  The row's terms stream through a private shared-memory ring
 // (cp.async, kSumStage nodes = 4 KB per stage, the next stage in flight while this one is added
