@@ -46,6 +46,18 @@ def test_host_libm_selfcheck():
     assert b"libm" in lib.noa_dcs_strerror(-5)
 
 
+def test_table_workspace_size_is_pure_arithmetic():
+    """noa_dcs_table_workspace_doubles needs no device: row parameters (2 x double2 per row), the
+    queue words, and 16 B per node and process with the node count rounded up to whole 6-point
+    cells."""
+    from noa_b200 import _lib
+    lib = _lib.load()
+    assert lib.noa_dcs_table_workspace_doubles(0, 180) == 0
+    assert lib.noa_dcs_table_workspace_doubles(10, 0) == 0
+    for n, mp, nodes in ((1, 1, 6), (10000, 1000, 1002), (1250, 180, 180), (37, 4000, 4002)):
+        assert lib.noa_dcs_table_workspace_doubles(n, mp) == 4 * n + 2 + 8 * n * nodes
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
