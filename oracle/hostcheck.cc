@@ -86,6 +86,21 @@ int hostcheck_dcs(int process, const double *K, const double *q, double *out, in
     return 0;
 }
 
+// pair production with the kinetic-energy-only part (PairRow: Lorentz factor, zeta) computed
+// separately and handed in, the way the table kernels hoist it out of the node loop
+int hostcheck_pair_with_row_part(const double *K, const double *q, double *out, int64_t n, double A,
+                                 double I, int32_t Z, double mass) {
+    const Params p = make_params(A, I, Z, mass);
+    for (int64_t i = 0; i < n; i++) {
+        PlainOps dv;
+        PairRow row;
+        row.gamma = pair_gamma(K[i], p, dv);
+        row.zeta = pair_zeta(row.gamma, p, kT, dv);
+        out[i] = pair_production(K[i], q[i], p, kT, dv, &row);
+    }
+    return 0;
+}
+
 int hostcheck_ionisation_closed_form(int integrand, const double *K, double *out, int64_t n,
                                      double xlow, double A, double I, int32_t Z, double mass) {
     const Params p = make_params(A, I, Z, mass);

@@ -32,6 +32,25 @@ def test_kernel_math_on_host_matches_oracle_bit_for_bit(hostcheck, port):
                 assert np.array_equal(out, want, equal_nan=True), (kind, en, p)
 
 
+def test_pair_production_with_hoisted_row_part_on_host(hostcheck, port, special):
+    """The table kernels compute pair production's Lorentz factor and zeta once per row and hand
+    them to every node's evaluation (dcs_math.cuh: PairRow): the same bits as the oracle, on the
+    synthetic sets and on the special-value grid (thresholds, zeros, huge values, NaN)."""
+    from conftest import SPECIAL_ELEMENTS
+    cases = [(grids.set_a(1 << 14), ELEMENTS, None), (grids.set_b(1 << 14), ELEMENTS, None),
+             ((special["S_K"], special["S_q"]), {e: ELEMENTS[e] for e in SPECIAL_ELEMENTS}, special)]
+    for (K, q), elements, golden in cases:
+        for en, el in elements.items():
+            out = np.zeros_like(K)
+            rc = hostcheck.hostcheck_pair_with_row_part(
+                _p(K), _p(q), _p(out), ctypes.c_int64(K.size), ctypes.c_double(el[0]),
+                ctypes.c_double(el[1]), ctypes.c_int32(el[2]), ctypes.c_double(MUON_MASS))
+            assert rc == 0
+            want = port.vmap(1, K, q, el, MUON_MASS, threads=4) if golden is None \
+                else golden[f"vmap_S_{en}_pair_production"]
+            assert np.array_equal(out, want, equal_nan=True), en
+
+
 def test_closed_form_ionisation_on_host(hostcheck, port):
     K = grids.table_energies(256, -2.0, 1.0)     # below the 10.8 GeV switch (dcs.hh:964)
     el = ELEMENTS["rock"]
