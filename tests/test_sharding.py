@@ -51,6 +51,41 @@ def test_sweep_segments_cover_every_pair_once():
     assert sweep_segments(1 << 26, 4, 3, 8) == [(1, 1 << 25, 1 << 26)]
 
 
+def test_partition_properties_hold_for_arbitrary_sizes():
+    """Property form of the two tests above (hypothesis): any pair count, any world size, any
+    material weights -- the shards tile the work exactly and carry equal cost up to one pair."""
+    from hypothesis import given, settings, strategies as st
+    from noa_b200.sharding import shard_range, sweep_segments
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 1 << 40), st.integers(1, 64))
+    def ranges(n, world):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 1 << 30), st.lists(st.integers(1, 4), min_size=1, max_size=6),
+           st.integers(1, 16))
+    def sweeps(n_mat, weights, world):
+        covered, cost = [], []
+        for r in range(world):
+            segs = sweep_segments(n_mat, weights, r, world)
+            for m, lo, hi in segs:
+                assert 0 <= m < len(weights) and 0 <= lo < hi <= n_mat
+                covered.append((m * n_mat + lo, m * n_mat + hi))
+            cost.append(sum(weights[m] * (hi - lo) for m, lo, hi in segs))
+        covered.sort()
+        assert covered[0][0] == 0 and covered[-1][1] == n_mat * len(weights)
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        assert max(cost) - min(cost) <= 2 * max(weights)
+
+    ranges()
+    sweeps()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
