@@ -2,8 +2,8 @@
 """Flat form through the C ABI with a preallocated workspace (no allocator in the timed region)."""
 import ctypes, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
-from noa_b200 import _lib, dcs, grids, STANDARD_ROCK, MUON_MASS
+import torch
+from noa_b200 import _lib, grids, MUON_MASS
 lib = _lib.require_device(); vp = ctypes.c_void_p
 out = {}
 Kall = torch.from_numpy(grids.table_energies(10000)).cuda()

@@ -4,7 +4,7 @@ shares (what one rank of W builds), per process, with a bit comparison of the tw
 Usage: [NOA_DCS_LIB=<lib>] python tools/flat_perf.py"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from noa_b200 import dcs, grids, STANDARD_ROCK, MUON_MASS
 
 def t(fn, reps=8, warm=2):

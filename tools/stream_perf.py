@@ -1,6 +1,6 @@
-import os, sys, json
+import sys
 sys.path.insert(0, "/root/repo")
-import numpy as np, torch
+import torch
 from noa_b200 import dcs, grids, STANDARD_ROCK, MUON_MASS
 def timeit(fn, reps=20, warm=3):
     for _ in range(warm): fn()

@@ -6,7 +6,7 @@ back-to-back builds each, CUDA events, max over ranks.  NOA_DCS_LIB selects a va
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
-from noa_b200 import dcs, grids, sharding, _lib, STANDARD_ROCK, MUON_MASS
+from noa_b200 import grids, sharding, STANDARD_ROCK, MUON_MASS
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
